@@ -1,0 +1,31 @@
+# Build everything in-tree.  sm_100a only: there is no other code path.
+NVCC      ?= nvcc
+CC        ?= gcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := -O3 -std=c++17 $(ARCH) -lineinfo -fmad=false -cudart static \
+             -Xcompiler -fPIC,-ffp-contract=off,-Wall,-Wno-unused-function
+LIBDIR    := voice_synth_b200/lib
+LIB       := $(LIBDIR)/libvoicesynth_cuda.so
+CSRC      := voice_synth_b200/csrc
+SRCS      := $(CSRC)/vs_api.cu $(CSRC)/vs_kernels.cu
+HDRS      := include/voicesynth.h $(CSRC)/vs_internal.h $(CSRC)/vs_presets.h
+
+all: lib host oracle
+
+lib: $(LIB)
+$(LIB): $(SRCS) $(HDRS)
+	mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRCS)
+
+host: lib
+	$(MAKE) -C host
+
+oracle:
+	$(MAKE) -C oracle all
+
+ptxas-info:
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o /dev/null $(CSRC)/vs_kernels.cu
+
+clean:
+	rm -rf $(LIBDIR) host/bin oracle/_build
+.PHONY: all lib host oracle clean ptxas-info

@@ -1,0 +1,884 @@
+/* vs_api.cu -- host side of libvoicesynth_cuda: context, parameter validation, cosine tables,
+ * time-chunk planning, kernel launches and (for host buffers) slab-pipelined PCIe copies.
+ *
+ * What stays on the host, and why it is still bit-exact with the reference:
+ *   - nSamples / P / T2 per stream: three scalar expressions (flowgen_shimmer.c:242,244,317) evaluated
+ *     here with the same C types; x86-64 has no FMA contraction by default and the file is built
+ *     with -ffp-contract=off.
+ *   - cos(PI*i/T2) tables, one per distinct T2 of the batch, computed with the system libm exactly
+ *     as the reference evaluates them (PI = 4.0*atan(1.0), flowgen_shimmer.c:39,319,328).  The
+ *     kernels only ever multiply/add/ceil these doubles, so the int16 pulse cannot differ by an ulp
+ *     of a device cosine.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/voicesynth.h"
+#include "vs_internal.h"
+#include "vs_presets.h"
+
+enum { VS_MODE_FLOW = 0, VS_MODE_SYNTH = 1, VS_MODE_FILTER = 2 };
+cudaError_t vs_launch_plan(const VsPlanArgs &a, bool want_log, cudaStream_t s);
+cudaError_t vs_launch_render(const VsRenderArgs &a, int mode, bool noise, bool exact, cudaStream_t s);
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct Slot {
+    int dev = 0;
+    int sm_count = 148;
+    cudaStream_t compute = nullptr;
+    bool own_compute = true;
+    cudaStream_t copy = nullptr;
+    cudaEvent_t h2d_done = nullptr;
+    cudaEvent_t slab_done[2] = {nullptr, nullptr};   /* D2H of the slab using pcm[k] finished */
+    cudaEvent_t slab_ready = nullptr;                /* render of the current slab finished   */
+    DevBuf streams, chunks, table, snap, nper, costab, coef, status, pcm[2], raw[2], flowin[2], log;
+    PinBuf h_streams, h_chunks, h_nper, h_status;
+    size_t costab_uploaded = 0;
+    std::vector<cudaEvent_t> tev;                    /* timing events (slot 0 only) */
+    size_t tev_used = 0;
+};
+
+} // namespace
+
+struct vs_ctx {
+    std::vector<Slot> slots;
+    double opt_chunk = 0;        /* 0 auto, <0 never, >0 fixed */
+    double opt_tol = 1e-13;
+    int opt_exact = 0;
+    int opt_slab = 0;
+    double opt_warps = 2.0;
+    int opt_long_scan = 1;
+    std::vector<double> cos_host;
+    std::map<int, uint32_t> cos_index;
+    int warm[VS_NUM_PRESETS];    /* warm-up samples per preset at opt_tol (gain-independent part) */
+    std::string err;
+    vs_timing timing;
+    bool timing_pending = false;
+};
+
+namespace {
+
+int fail(vs_ctx *c, int code, const char *fmt, ...)
+{
+    if (c) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        c->err = buf;
+    }
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, VS_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+int dev_reserve(vs_ctx *ctx, Slot &s, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return VS_OK;
+    if (b.p) {
+        CU(cudaStreamSynchronize(s.compute));
+        CU(cudaStreamSynchronize(s.copy));
+        CU(cudaFree(b.p));
+        b.p = nullptr; b.cap = 0;
+    }
+    size_t cap = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, cap);
+    if (e != cudaSuccess) { b.p = nullptr; return fail(ctx, VS_ENOMEM, "cudaMalloc(%zu) failed: %s", cap, cudaGetErrorString(e)); }
+    b.cap = cap;
+    return VS_OK;
+}
+
+int pin_reserve(vs_ctx *ctx, PinBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return VS_OK;
+    if (b.p) { cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
+    size_t cap = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaHostAlloc(&b.p, cap, cudaHostAllocDefault);
+    if (e != cudaSuccess) { b.p = nullptr; return fail(ctx, VS_ENOMEM, "cudaHostAlloc(%zu) failed: %s", cap, cudaGetErrorString(e)); }
+    b.cap = cap;
+    return VS_OK;
+}
+
+/* ---- parameter access with the reference defaults (flowgen_shimmer.c:87, vowel_new.c:76-77) ---- */
+struct FlowRow {
+    float dur, jitter, shimmer, cq, K, Kvar, F0, DC, noise;
+    int32_t amp, fs;
+    uint8_t flags;
+    uint32_t seed;
+};
+
+FlowRow flow_row(const vs_flow_params *p, size_t i)
+{
+    FlowRow r;
+    r.dur = p && p->dur ? p->dur[i] : 1.0f;
+    r.jitter = p && p->jitter ? p->jitter[i] : 0.0f;
+    r.shimmer = p && p->shimmer ? p->shimmer[i] : 0.0f;
+    r.cq = p && p->cq ? p->cq[i] : 0.55f;
+    r.K = p && p->K ? p->K[i] : 0.65f;
+    r.Kvar = p && p->Kvar ? p->Kvar[i] : 0.0f;
+    r.F0 = p && p->F0 ? p->F0[i] : 120.0f;
+    r.DC = p && p->DC ? p->DC[i] : 0.0f;
+    r.noise = p && p->noise ? p->noise[i] : 0.0f;
+    r.amp = p && p->amp ? p->amp[i] : 12000;
+    r.fs = p && p->fs ? p->fs[i] : 22050;
+    r.flags = p && p->flags ? p->flags[i] : 0;
+    r.seed = p && p->seed ? p->seed[i] : 1u;
+    return r;
+}
+
+uint64_t row_nsamples(const FlowRow &r)
+{
+    /* `(unsigned long) par.fs*par.dur`: unsigned long * float is a float product (:242) */
+    volatile float prod = (float)(uint64_t)(int64_t)r.fs * r.dur;
+    if (!(prod >= 0.0f) || prod >= 1.8e19f) return 0;
+    return (uint64_t)prod;
+}
+
+int row_P(const FlowRow &r)
+{
+    volatile float q = (float)(int64_t)r.fs / r.F0;                   /* :244 */
+    if (!(q > -2147483648.0f && q < 2147483648.0f)) return 0;
+    return (int)q;
+}
+
+int row_T2(const FlowRow &r, int P)
+{
+    volatile double h = 0.5 * (double)r.cq;                           /* :317 */
+    volatile double v = h * P;
+    return (int)std::ceil(v);
+}
+
+int row_validate(const FlowRow &r)
+{
+    if (!(r.fs > 0) || !std::isfinite(r.dur) || !(r.dur > 0.0f)) return VS_ERANGE;
+    if (!std::isfinite(r.F0) || !(r.F0 > 0.0f)) return VS_ERANGE;
+    const int P = row_P(r);
+    if (P < 1 || P > 32000) return VS_ERANGE;                        /* T is stored in a short (:289) */
+    const uint64_t n = row_nsamples(r);
+    if (n < 1 || n > 0x7fffffffull) return VS_ERANGE;
+    if (!(r.jitter >= 0.0f && r.jitter <= 10.0f)) return VS_ERANGE;   /* :478 */
+    if (!(r.shimmer >= 0.0f && r.shimmer <= 1.0f)) return VS_ERANGE;  /* :544 */
+    if (!(r.cq >= 0.0f && r.cq <= 1.0f)) return VS_ERANGE;            /* :490 */
+    if (!std::isfinite(r.K) || !(r.K >= 0.0f)) return VS_ERANGE;
+    if (!(r.Kvar >= 0.0f && r.Kvar <= 1.0f)) return VS_ERANGE;        /* :530 */
+    if (!(r.amp >= 0 && r.amp < 32767)) return VS_ERANGE;             /* :518 */
+    if (!std::isfinite(r.DC) || !(r.DC >= 0.0f) || r.DC > 32767.0f) return VS_ERANGE;
+    if ((r.flags & VS_F_NOISE) && (!std::isfinite(r.noise) || !(r.noise > 0.0f))) return VS_ERANGE;
+    if (r.flags & ~(VS_F_JITTER | VS_F_SHIMMER | VS_F_NOISE)) return VS_EINVAL;
+    return VS_OK;
+}
+
+uint32_t row_max_periods(const FlowRow &r, uint64_t n, int P)
+{
+    const bool jit = (r.flags & VS_F_JITTER) && r.jitter != 0.0f;
+    int tmin = P;
+    if (jit) {
+        tmin = (int)std::floor(0.8f * (float)P);                      /* accepted T satisfy (float)T >= (float)0.8*P */
+        if (tmin < 1) tmin = 1;
+    }
+    return (uint32_t)(n / (uint64_t)tmin + 2);
+}
+
+int preset_index(int key)
+{
+    const char *q = key ? strchr(vs_preset_keys, key) : nullptr;
+    return q ? (int)(q - vs_preset_keys) : -1;
+}
+
+/* Samples after which the free response of an arbitrary unit-bounded initial state has decayed below
+ * tol: W = 1 + last n with sum_j |(Phi^n)[0][j]| >= tol, Phi the companion matrix of the preset. */
+int warmup_for(const double *A, double tol)
+{
+    const int N = VS_ORDER;
+    /* column j holds the free response state started from unit vector e_j */
+    std::vector<double> st(N * N, 0.0);
+    for (int j = 0; j < N; j++) st[j * N + j] = 1.0;       /* st[j*N + k] = y[n-1-k] of response j */
+    int last = 0;
+    const int horizon = 60000;
+    int quiet = 0;
+    for (int n = 0; n < horizon; n++) {
+        double g = 0.0;
+        for (int j = 0; j < N; j++) {
+            double *s = &st[j * N];
+            double y0 = 0.0;
+            for (int k = 0; k < N; k++) y0 -= A[k + 1] * s[k];
+            for (int k = N - 1; k > 0; k--) s[k] = s[k - 1];
+            s[0] = y0;
+            g += std::fabs(y0);
+        }
+        if (g >= tol) { last = n + 1; quiet = 0; }
+        else if (++quiet > 4096) break;
+    }
+    return last + 1;
+}
+
+void compute_warmups(vs_ctx *ctx)
+{
+    for (int k = 0; k < VS_NUM_PRESETS; k++) ctx->warm[k] = warmup_for(vs_preset_den[k], ctx->opt_tol);
+}
+
+uint32_t cos_table_for(vs_ctx *ctx, int T2)
+{
+    auto it = ctx->cos_index.find(T2);
+    if (it != ctx->cos_index.end()) return it->second;
+    const uint32_t off = (uint32_t)ctx->cos_host.size();
+    volatile double one = 1.0;
+    const double pi = 4.0 * std::atan(one);                           /* #define PI 4.0*atan(1.0) (:39) */
+    for (int i = 0; i < T2; i++) {
+        volatile double num = pi * i;                                 /* PI*i/T2 == ((4.0*atan(1.0))*i)/T2 */
+        volatile double arg = num / T2;
+        ctx->cos_host.push_back(std::cos(arg));
+    }
+    ctx->cos_index[T2] = off;
+    return off;
+}
+
+enum PtrKind { PK_HOST_PAGEABLE, PK_HOST_PINNED, PK_DEVICE };
+
+PtrKind classify(const void *p, int *dev_out)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return PK_HOST_PAGEABLE; }
+    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) { if (dev_out) *dev_out = at.device; return PK_DEVICE; }
+    if (at.type == cudaMemoryTypeHost) return PK_HOST_PINNED;
+    return PK_HOST_PAGEABLE;
+}
+
+cudaEvent_t timing_event(Slot &s)
+{
+    if (s.tev_used == s.tev.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        s.tev.push_back(e);
+    }
+    return s.tev[s.tev_used++];
+}
+
+struct Batch {
+    int mode;
+    size_t n;
+    const vs_flow_params *fp;
+    const vs_filter_params *ff;
+    const int16_t *flow_in;
+    const uint64_t *in_offsets;
+    const uint64_t *nsamp;
+    int16_t *pcm_out;
+    const uint64_t *offsets;
+    double *raw_out;
+    vs_period_log *log;
+};
+
+/* Choose the time-chunk length for a group of streams (SURVEY.md 7 "Occupancy"): enough chunks to
+ * give every SM sub-partition `opt_warps` warps, but never shorter than the carry warm-up costs. */
+uint32_t choose_chunk(vs_ctx *ctx, const Slot &slot, int mode, size_t n_streams, uint64_t total, double avg_warm)
+{
+    if (ctx->opt_chunk < 0) return 0;
+    if (mode != VS_MODE_FLOW && ctx->opt_exact) return 0;
+    if (ctx->opt_chunk > 0) {
+        uint32_t L = (uint32_t)ctx->opt_chunk;
+        L = (L + 7u) & ~7u;
+        return L < 64 ? 64 : L;
+    }
+    const double want_threads = (double)slot.sm_count * 4.0 * 32.0 * ctx->opt_warps;
+    if ((double)n_streams >= want_threads) return 0;
+    double L = std::ceil((double)total / want_threads);
+    /* with a filter, every chunk but the first pays avg_warm extra samples: do not go below it */
+    const double floor_len = (mode == VS_MODE_FLOW) ? 1024.0 : std::max(2048.0, 1.5 * avg_warm);
+    if (L < floor_len) L = floor_len;
+    uint32_t Li = ((uint32_t)L + 7u) & ~7u;
+    return Li;
+}
+
+int run_batch(vs_ctx *ctx, const Batch &b)
+{
+    if (!ctx) return VS_EINVAL;
+    if (b.n == 0) return VS_OK;
+    if (!b.pcm_out) return fail(ctx, VS_EINVAL, "pcm_out is NULL");
+    if (b.mode == VS_MODE_FILTER && (!b.flow_in || !b.nsamp)) return fail(ctx, VS_EINVAL, "flow_in/nsamp is NULL");
+    if (b.n > 0x7fffffffull) return fail(ctx, VS_EINVAL, "too many streams");
+    const size_t n = b.n;
+    const bool want_log = b.log && b.log->rec && b.log->rec_offsets && b.mode != VS_MODE_FILTER;
+
+    /* ---- 1. per-stream descriptors ---------------------------------------------------------- */
+    std::vector<VsStream> hs(n);
+    uint64_t max_n = 0;
+    bool any_noise = false;
+    for (size_t i = 0; i < n; i++) {
+        VsStream &s = hs[i];
+        memset(&s, 0, sizeof s);
+        if (b.mode == VS_MODE_FILTER) {
+            if (b.nsamp[i] > 0x7fffffffull) return fail(ctx, VS_EOVERLAP, "stream %zu: too many samples", i);
+            s.n = (uint32_t)b.nsamp[i];
+        } else {
+            const FlowRow r = flow_row(b.fp, i);
+            const int rc = row_validate(r);
+            if (rc) return fail(ctx, rc, "stream %zu: flow parameter out of range", i);
+            s.n = (uint32_t)row_nsamples(r);
+            s.P = row_P(r);
+            s.T2 = row_T2(r, s.P);
+            s.cos_off = cos_table_for(ctx, s.T2);
+            s.amp = r.amp; s.DC = r.DC; s.jitter = r.jitter; s.shimmer = r.shimmer; s.K = r.K; s.Kvar = r.Kvar;
+            s.noise = r.noise; s.seed = r.seed; s.flags = r.flags;
+            s.DCs = (int16_t)(int32_t)r.DC;                            /* x[i] = par.DC (:321,:335) */
+            s.tab_cap = row_max_periods(r, s.n, s.P);
+            any_noise |= (r.flags & VS_F_NOISE) != 0;
+        }
+        if (b.mode != VS_MODE_FLOW) {
+            const int key = b.ff && b.ff->preset ? b.ff->preset[i] : 'a';
+            const int pi = preset_index(key);
+            if (pi < 0) return fail(ctx, VS_EPRESET, "stream %zu: unknown vowel preset 0x%02x", i, key);
+            s.preset = (uint8_t)pi;
+            s.gain = b.ff && b.ff->gain ? b.ff->gain[i] : 10.0f;
+            s.pre = b.ff && b.ff->pre ? b.ff->pre[i] : 1.0f;
+            if (!std::isfinite(s.gain) || !std::isfinite(s.pre)) return fail(ctx, VS_ERANGE, "stream %zu: gain/pre not finite", i);
+        }
+        max_n = std::max<uint64_t>(max_n, s.n);
+    }
+    for (size_t i = 0; i < n; i++) {
+        hs[i].out_off = b.offsets ? b.offsets[i] : (uint64_t)i * max_n;
+        if (b.mode == VS_MODE_FILTER) hs[i].in_off = b.in_offsets ? b.in_offsets[i] : (uint64_t)i * max_n;
+        if (want_log) hs[i].log_off = b.log->rec_offsets[i];
+    }
+
+    /* ---- 2. where do the buffers live ------------------------------------------------------- */
+    int odev = -1;
+    const PtrKind out_kind = classify(b.pcm_out, &odev);
+    const PtrKind raw_kind = b.raw_out ? classify(b.raw_out, nullptr) : out_kind;
+    const PtrKind in_kind = b.flow_in ? classify(b.flow_in, nullptr) : out_kind;
+    const bool out_dev = out_kind == PK_DEVICE;
+    if ((b.raw_out && (raw_kind == PK_DEVICE) != out_dev) || (b.flow_in && (in_kind == PK_DEVICE) != out_dev))
+        return fail(ctx, VS_EINVAL, "pcm/raw/flow buffers must be all host or all device");
+    if (out_dev && ctx->slots.size() != 1) return fail(ctx, VS_EINVAL, "device buffers need a single-device ctx");
+    if (out_dev && odev != ctx->slots[0].dev) return fail(ctx, VS_EINVAL, "device buffer lives on device %d, ctx on %d", odev, ctx->slots[0].dev);
+
+    /* ---- 3. contiguous stream ranges per device slot, balanced by samples ------ */
+    const size_t nslots = ctx->slots.size();
+    std::vector<size_t> cut(nslots + 1, n);
+    {
+        uint64_t total = 0;
+        for (size_t i = 0; i < n; i++) total += hs[i].n;
+        cut[0] = 0;
+        uint64_t acc = 0;
+        size_t g = 1;
+        for (size_t i = 0; i < n && g < nslots; i++) {
+            acc += hs[i].n;
+            while (g < nslots && acc * nslots >= total * g) cut[g++] = i + 1;
+        }
+    }
+
+    memset(&ctx->timing, 0, sizeof ctx->timing);
+    ctx->timing_pending = true;
+    const bool exact = ctx->opt_exact != 0;
+
+    /* ---- 4. per slot: descriptors up, then slabs of plan -> render -> copy ------------------- */
+    for (size_t g = 0; g < nslots; g++) {
+        Slot &sl = ctx->slots[g];
+        const size_t s0 = cut[g], s1 = cut[g + 1];
+        if (s1 <= s0) continue;
+        const size_t ns = s1 - s0;
+        CU(cudaSetDevice(sl.dev));
+        if (g == 0) sl.tev_used = 0;
+
+        uint64_t total = 0;
+        double warm_sum = 0.0;
+        for (size_t i = s0; i < s1; i++) {
+            total += hs[i].n;
+            if (b.mode != VS_MODE_FLOW) warm_sum += ctx->warm[hs[i].preset];
+        }
+        /* slabs: groups of consecutive streams that are launched and copied together */
+        size_t slab_streams = ns;
+        if (!out_dev) {
+            if (ctx->opt_slab > 0) slab_streams = (size_t)ctx->opt_slab;
+            else {
+                const uint64_t bytes = total * 2;
+                size_t want = (size_t)std::min<uint64_t>(16, std::max<uint64_t>(1, bytes / (24ull << 20)));
+                slab_streams = (ns + want - 1) / want;
+            }
+            if (slab_streams < 1) slab_streams = 1;
+        }
+        const size_t n_slabs = (ns + slab_streams - 1) / slab_streams;
+
+        /* chunk plan */
+        std::vector<VsChunk> hc;
+        std::vector<size_t> slab_c0(n_slabs + 1, 0);
+        uint64_t tab_total = 0, warm_total = 0;
+        for (size_t k = 0; k < n_slabs; k++) {
+            const size_t a0 = s0 + k * slab_streams, a1 = std::min(s1, a0 + slab_streams);
+            uint64_t tot = 0;
+            double wsum = 0.0;
+            for (size_t i = a0; i < a1; i++) { tot += hs[i].n; if (b.mode != VS_MODE_FLOW) wsum += ctx->warm[hs[i].preset]; }
+            const uint32_t L = choose_chunk(ctx, sl, b.mode, a1 - a0, tot, wsum / (double)(a1 - a0));
+            slab_c0[k] = hc.size();
+            for (size_t i = a0; i < a1; i++) {
+                VsStream &s = hs[i];
+                const uint64_t base_addr = out_dev ? (reinterpret_cast<uintptr_t>(b.pcm_out) >> 1) + s.out_off : s.out_off;
+                /* host outputs are mirrored on the device at the same offsets relative to a 16-byte
+                 * aligned slab base, so the phase of a row is its sample offset mod 8 either way */
+                const uint32_t ph = (uint32_t)(base_addr & 7);
+                const uint32_t C = (L == 0 || s.n <= L) ? 1u : (uint32_t)((s.n + L - 1) / L);
+                s.chunk0 = (uint32_t)hc.size();
+                s.n_chunks = C;
+                s.tab_off = tab_total;
+                tab_total += s.tab_cap;
+                const uint32_t W = (b.mode == VS_MODE_FLOW) ? 0u : (uint32_t)ctx->warm[s.preset];
+                for (uint32_t c = 0; c < C; c++) {
+                    VsChunk ck;
+                    memset(&ck, 0, sizeof ck);
+                    ck.stream = (uint32_t)(i - s0);
+                    ck.emit_lo = c == 0 ? 0u : c * L - ph;
+                    ck.emit_hi = c + 1 == C ? s.n : (c + 1) * L - ph;
+                    ck.gen_target = ck.emit_lo > W ? ck.emit_lo - W : 0u;
+                    if (c > 0) warm_total += ck.emit_lo - ck.gen_target;
+                    hc.push_back(ck);
+                }
+            }
+        }
+        slab_c0[n_slabs] = hc.size();
+        const size_t nc = hc.size();
+        ctx->timing.chunks += (uint32_t)nc;
+        ctx->timing.samples += total;
+        ctx->timing.warmup_samples += warm_total;
+
+        /* device memory */
+        int rc;
+        if ((rc = dev_reserve(ctx, sl, sl.streams, ns * sizeof(VsStream)))) return rc;
+        if ((rc = dev_reserve(ctx, sl, sl.chunks, nc * sizeof(VsChunk)))) return rc;
+        if ((rc = dev_reserve(ctx, sl, sl.nper, ns * sizeof(uint32_t)))) return rc;
+        if ((rc = dev_reserve(ctx, sl, sl.status, sizeof(int32_t)))) return rc;
+        if (b.mode != VS_MODE_FILTER) {
+            if ((rc = dev_reserve(ctx, sl, sl.table, tab_total * sizeof(VsPeriod)))) return rc;
+            if (any_noise && (rc = dev_reserve(ctx, sl, sl.snap, nc * 32 * sizeof(uint32_t)))) return rc;
+            if ((rc = dev_reserve(ctx, sl, sl.costab, std::max<size_t>(8, ctx->cos_host.size() * sizeof(double))))) return rc;
+            if (sl.costab_uploaded != ctx->cos_host.size()) {
+                /* tables only ever grow; a synchronous copy keeps the host vector free to grow again */
+                CU(cudaStreamSynchronize(sl.compute));
+                CU(cudaMemcpy(sl.costab.p, ctx->cos_host.data(), ctx->cos_host.size() * sizeof(double), cudaMemcpyHostToDevice));
+                sl.costab_uploaded = ctx->cos_host.size();
+            }
+        }
+        if ((rc = pin_reserve(ctx, sl.h_streams, ns * sizeof(VsStream)))) return rc;
+        if ((rc = pin_reserve(ctx, sl.h_chunks, nc * sizeof(VsChunk)))) return rc;
+        if ((rc = pin_reserve(ctx, sl.h_nper, ns * sizeof(uint32_t)))) return rc;
+        if ((rc = pin_reserve(ctx, sl.h_status, sizeof(int32_t)))) return rc;
+
+        /* log span of this slot */
+        uint64_t log_lo = 0, log_hi = 0;
+        if (want_log) {
+            log_lo = b.log->rec_offsets[s0];
+            log_hi = b.log->rec_offsets[s1];
+            for (size_t i = s0; i < s1; i++) {
+                if (b.log->rec_offsets[i + 1] < b.log->rec_offsets[i] || b.log->rec_offsets[i + 1] - b.log->rec_offsets[i] < hs[i].tab_cap)
+                    return fail(ctx, VS_EINVAL, "stream %zu: period log too small (need %u records)", i, hs[i].tab_cap);
+                hs[i].log_off = b.log->rec_offsets[i] - log_lo;
+            }
+            if ((rc = dev_reserve(ctx, sl, sl.log, std::max<uint64_t>(1, log_hi - log_lo) * sizeof(vs_period_rec)))) return rc;
+            CU(cudaMemsetAsync(sl.log.p, 0, (log_hi - log_lo) * sizeof(vs_period_rec), sl.compute));
+        }
+
+        /* device-side offsets: rows of a slab live at (offset - slab_min) + pad to keep the phase */
+        struct SlabGeom { uint64_t out_min, out_max, in_min, in_max; };
+        std::vector<SlabGeom> geom(n_slabs);
+        uint64_t span_max = 0, in_span_max = 0;
+        for (size_t k = 0; k < n_slabs; k++) {
+            const size_t a0 = s0 + k * slab_streams, a1 = std::min(s1, a0 + slab_streams);
+            SlabGeom gm = {~0ull, 0, ~0ull, 0};
+            for (size_t i = a0; i < a1; i++) {
+                gm.out_min = std::min(gm.out_min, hs[i].out_off);
+                gm.out_max = std::max(gm.out_max, hs[i].out_off + hs[i].n);
+                gm.in_min = std::min(gm.in_min, hs[i].in_off);
+                gm.in_max = std::max(gm.in_max, hs[i].in_off + hs[i].n);
+            }
+            gm.out_min &= ~7ull;                                      /* keep (offset mod 8) on the device */
+            gm.in_min &= ~7ull;
+            geom[k] = gm;
+            span_max = std::max(span_max, gm.out_max - gm.out_min);
+            in_span_max = std::max(in_span_max, gm.in_max - gm.in_min);
+        }
+        if (!out_dev) {
+            for (int d = 0; d < (n_slabs > 1 ? 2 : 1); d++) {
+                if ((rc = dev_reserve(ctx, sl, sl.pcm[d], span_max * sizeof(int16_t) + 64))) return rc;
+                if (b.raw_out && (rc = dev_reserve(ctx, sl, sl.raw[d], span_max * sizeof(double) + 64))) return rc;
+                if (b.mode == VS_MODE_FILTER && (rc = dev_reserve(ctx, sl, sl.flowin[d], in_span_max * sizeof(int16_t) + 64))) return rc;
+            }
+        }
+
+        /* upload descriptors; the previous call on this slot must be done with the staging buffers
+         * (everything above overlapped with it) */
+        CU(cudaEventSynchronize(sl.h2d_done));
+        VsStream *ps = (VsStream *)sl.h_streams.p;
+        for (size_t k = 0; k < n_slabs; k++) {
+            const size_t a0 = s0 + k * slab_streams, a1 = std::min(s1, a0 + slab_streams);
+            for (size_t i = a0; i < a1; i++) {
+                ps[i - s0] = hs[i];
+                if (!out_dev) {
+                    ps[i - s0].out_off = hs[i].out_off - geom[k].out_min;
+                    ps[i - s0].in_off = hs[i].in_off - geom[k].in_min;
+                }
+            }
+        }
+        memcpy(sl.h_chunks.p, hc.data(), nc * sizeof(VsChunk));
+        *(int32_t *)sl.h_status.p = 0;
+        CU(cudaMemcpyAsync(sl.streams.p, sl.h_streams.p, ns * sizeof(VsStream), cudaMemcpyHostToDevice, sl.compute));
+        CU(cudaMemcpyAsync(sl.chunks.p, sl.h_chunks.p, nc * sizeof(VsChunk), cudaMemcpyHostToDevice, sl.compute));
+        CU(cudaMemsetAsync(sl.status.p, 0, sizeof(int32_t), sl.compute));
+
+        cudaEvent_t t_first = nullptr;
+        if (g == 0) { t_first = timing_event(sl); CU(cudaEventRecord(t_first, sl.compute)); }
+
+        for (size_t k = 0; k < n_slabs; k++) {
+            const size_t a0 = s0 + k * slab_streams, a1 = std::min(s1, a0 + slab_streams);
+            const size_t c0 = slab_c0[k], c1 = slab_c0[k + 1];
+            const int d = (int)(k & 1);
+            int16_t *d_pcm = out_dev ? b.pcm_out : (int16_t *)sl.pcm[d].p;
+            double *d_raw = b.raw_out ? (out_dev ? b.raw_out : (double *)sl.raw[d].p) : nullptr;
+            const int16_t *d_in = nullptr;
+
+            if (!out_dev && k >= 2) CU(cudaStreamWaitEvent(sl.compute, sl.slab_done[d], 0));
+
+            if (b.mode == VS_MODE_FILTER) {
+                if (out_dev) d_in = b.flow_in;
+                else {
+                    d_in = (const int16_t *)sl.flowin[d].p;
+                    CU(cudaMemcpyAsync(sl.flowin[d].p, b.flow_in + geom[k].in_min, (geom[k].in_max - geom[k].in_min) * sizeof(int16_t),
+                                       cudaMemcpyHostToDevice, sl.compute));
+                }
+            }
+
+            cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+            if (g == 0) { e0 = timing_event(sl); e1 = timing_event(sl); e2 = timing_event(sl); CU(cudaEventRecord(e0, sl.compute)); }
+
+            if (b.mode != VS_MODE_FILTER) {
+                VsPlanArgs pa;
+                memset(&pa, 0, sizeof pa);
+                pa.streams = (const VsStream *)sl.streams.p + (a0 - s0);
+                pa.n_streams = (uint32_t)(a1 - a0);
+                pa.chunks = (VsChunk *)sl.chunks.p;
+                pa.table = (VsPeriod *)sl.table.p;
+                pa.rng_snap = any_noise ? (uint32_t *)sl.snap.p : nullptr;
+                pa.n_periods = (uint32_t *)sl.nper.p + (a0 - s0);
+                pa.costab = (const double *)sl.costab.p;
+                pa.log = want_log ? sl.log.p : nullptr;
+                pa.status = (int32_t *)sl.status.p;
+                pa.need_pulse = want_log;
+                CU(vs_launch_plan(pa, want_log, sl.compute));
+                ctx->timing.launches++;
+            }
+            if (g == 0) CU(cudaEventRecord(e1, sl.compute));
+
+            VsRenderArgs ra;
+            memset(&ra, 0, sizeof ra);
+            ra.streams = (const VsStream *)sl.streams.p;
+            ra.chunks = (const VsChunk *)sl.chunks.p + c0;
+            ra.n_chunks = (uint32_t)(c1 - c0);
+            ra.table = (const VsPeriod *)sl.table.p;
+            ra.rng_snap = any_noise ? (const uint32_t *)sl.snap.p + c0 * 32 : nullptr;
+            ra.costab = (const double *)sl.costab.p;
+            ra.coef = (const double *)sl.coef.p;
+            ra.flow_in = d_in;
+            ra.pcm_out = d_pcm;
+            ra.raw_out = d_raw;
+            CU(vs_launch_render(ra, b.mode, any_noise, exact, sl.compute));
+            ctx->timing.launches++;
+            if (g == 0) CU(cudaEventRecord(e2, sl.compute));
+
+            if (!out_dev) {
+                /* PCM home over PCIe on the copy stream while the next slab renders */
+                CU(cudaEventRecord(sl.slab_ready, sl.compute));
+                CU(cudaStreamWaitEvent(sl.copy, sl.slab_ready, 0));
+                /* merge rows that touch into runs: a dense batch is one copy per slab */
+                uint64_t run_lo = hs[a0].out_off, run_hi = hs[a0].out_off + hs[a0].n;
+                auto flush = [&](uint64_t lo, uint64_t hi) -> cudaError_t {
+                    cudaError_t e = cudaMemcpyAsync(b.pcm_out + lo, d_pcm + (lo - geom[k].out_min), (hi - lo) * sizeof(int16_t),
+                                                    cudaMemcpyDeviceToHost, sl.copy);
+                    if (e == cudaSuccess && b.raw_out)
+                        e = cudaMemcpyAsync(b.raw_out + lo, d_raw + (lo - geom[k].out_min), (hi - lo) * sizeof(double),
+                                            cudaMemcpyDeviceToHost, sl.copy);
+                    return e;
+                };
+                for (size_t i = a0 + 1; i < a1; i++) {
+                    if (hs[i].out_off == run_hi) run_hi += hs[i].n;
+                    else { CU(flush(run_lo, run_hi)); run_lo = hs[i].out_off; run_hi = run_lo + hs[i].n; }
+                }
+                CU(flush(run_lo, run_hi));
+                CU(cudaEventRecord(sl.slab_done[d], sl.copy));
+            }
+        }
+        if (want_log)
+            CU(cudaMemcpyAsync(b.log->rec + log_lo, sl.log.p, (log_hi - log_lo) * sizeof(vs_period_rec), cudaMemcpyDeviceToHost, sl.compute));
+        if (want_log && b.log->count)
+            CU(cudaMemcpyAsync(sl.h_nper.p, sl.nper.p, ns * sizeof(uint32_t), cudaMemcpyDeviceToHost, sl.compute));
+        CU(cudaMemcpyAsync(sl.h_status.p, sl.status.p, sizeof(int32_t), cudaMemcpyDeviceToHost, sl.compute));
+        if (!out_dev) CU(cudaStreamWaitEvent(sl.compute, sl.slab_done[(n_slabs - 1) & 1], 0));
+        if (g == 0) { cudaEvent_t t_last = timing_event(sl); CU(cudaEventRecord(t_last, sl.compute)); }
+        CU(cudaEventRecord(sl.h2d_done, sl.compute));                 /* "call done" for this slot */
+    }
+
+    /* ---- 5. host buffers: the call returns when the data has landed -------------------------- */
+    if (!out_dev || want_log) {
+        const int rc = vs_sync(ctx);
+        if (rc) return rc;
+        if (want_log && b.log->count) {
+            for (size_t g = 0; g < nslots; g++) {
+                const size_t s0 = cut[g], s1 = cut[g + 1];
+                if (s1 > s0) memcpy(b.log->count + s0, ctx->slots[g].h_nper.p, (s1 - s0) * sizeof(uint32_t));
+            }
+        }
+    }
+    return VS_OK;
+}
+
+} // namespace
+
+/* ================================================================================================
+ * exported C ABI
+ * ============================================================================================== */
+extern "C" {
+
+int vs_abi_version(void) { return VS_ABI_VERSION; }
+
+int vs_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *vs_strerror(int code)
+{
+    switch (code) {
+    case VS_OK: return "ok";
+    case VS_EINVAL: return "invalid argument";
+    case VS_ERANGE: return "stream parameter out of range";
+    case VS_EPRESET: return "unknown vowel preset";
+    case VS_ENOMEM: return "out of memory";
+    case VS_ECUDA: return "CUDA error";
+    case VS_ENODEV: return "no usable sm_100 device";
+    case VS_EOVERLAP: return "bad output layout";
+    default: return "unknown error";
+    }
+}
+
+const char *vs_last_error(vs_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
+
+int vs_ctx_create(vs_ctx **out, const int *devices, int n_devices, uint32_t flags)
+{
+    (void)flags;
+    if (!out) return VS_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { cudaGetLastError(); return VS_ENODEV; }
+    std::vector<int> devs;
+    if (!devices || n_devices <= 0) devs.push_back(0);
+    else devs.assign(devices, devices + n_devices);
+    vs_ctx *ctx = new (std::nothrow) vs_ctx();
+    if (!ctx) return VS_ENOMEM;
+    compute_warmups(ctx);
+    std::vector<double> coef(VS_NUM_PRESETS * VS_RING, 0.0);
+    for (int k = 0; k < VS_NUM_PRESETS; k++)
+        for (int j = 0; j <= VS_ORDER; j++) coef[k * VS_RING + j] = vs_preset_den[k][j];
+    for (int d : devs) {
+        if (d < 0 || d >= count) { vs_ctx_destroy(ctx); return VS_ENODEV; }
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d) != cudaSuccess || prop.major != 10) {
+            /* the only code in the library is sm_100a SASS: anything else cannot run it */
+            cudaGetLastError();
+            vs_ctx_destroy(ctx);
+            return VS_ENODEV;
+        }
+        Slot s;
+        s.dev = d;
+        s.sm_count = prop.multiProcessorCount;
+        bool ok = cudaSetDevice(d) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&s.compute, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&s.slab_done[0], cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&s.slab_done[1], cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&s.slab_ready, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaMalloc(&s.coef.p, coef.size() * sizeof(double)) == cudaSuccess &&
+                  cudaMemcpy(s.coef.p, coef.data(), coef.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+        s.coef.cap = coef.size() * sizeof(double);
+        ctx->slots.push_back(s);
+        if (!ok) { cudaGetLastError(); vs_ctx_destroy(ctx); return VS_ECUDA; }
+    }
+    *out = ctx;
+    return VS_OK;
+}
+
+void vs_ctx_destroy(vs_ctx *ctx)
+{
+    if (!ctx) return;
+    for (Slot &s : ctx->slots) {
+        cudaSetDevice(s.dev);
+        if (s.compute) cudaStreamSynchronize(s.compute);
+        if (s.copy) cudaStreamSynchronize(s.copy);
+        DevBuf *bufs[] = {&s.streams, &s.chunks, &s.table, &s.snap, &s.nper, &s.costab, &s.coef, &s.status,
+                          &s.pcm[0], &s.pcm[1], &s.raw[0], &s.raw[1], &s.flowin[0], &s.flowin[1], &s.log};
+        for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+        PinBuf *pins[] = {&s.h_streams, &s.h_chunks, &s.h_nper, &s.h_status};
+        for (PinBuf *b : pins) if (b->p) cudaFreeHost(b->p);
+        for (cudaEvent_t e : s.tev) cudaEventDestroy(e);
+        if (s.h2d_done) cudaEventDestroy(s.h2d_done);
+        if (s.slab_done[0]) cudaEventDestroy(s.slab_done[0]);
+        if (s.slab_done[1]) cudaEventDestroy(s.slab_done[1]);
+        if (s.slab_ready) cudaEventDestroy(s.slab_ready);
+        if (s.copy) cudaStreamDestroy(s.copy);
+        if (s.compute && s.own_compute) cudaStreamDestroy(s.compute);
+    }
+    cudaGetLastError();
+    delete ctx;
+}
+
+int vs_ctx_set_option(vs_ctx *ctx, int option, double value)
+{
+    if (!ctx) return VS_EINVAL;
+    switch (option) {
+    case VS_OPT_CHUNK_SAMPLES: ctx->opt_chunk = value; return VS_OK;
+    case VS_OPT_CARRY_TOL:
+        if (!(value > 0.0 && value < 1.0)) return VS_EINVAL;
+        ctx->opt_tol = value; compute_warmups(ctx); return VS_OK;
+    case VS_OPT_EXACT_FILTER: ctx->opt_exact = value != 0.0; return VS_OK;
+    case VS_OPT_SLAB_STREAMS: ctx->opt_slab = value > 0 ? (int)value : 0; return VS_OK;
+    case VS_OPT_TARGET_WARPS: if (!(value > 0)) return VS_EINVAL; ctx->opt_warps = value; return VS_OK;
+    case VS_OPT_LONG_SCAN: ctx->opt_long_scan = value != 0.0; return VS_OK;
+    default: return VS_EINVAL;
+    }
+}
+
+int vs_ctx_set_stream(vs_ctx *ctx, int slot, void *cuda_stream)
+{
+    if (!ctx || slot < 0 || (size_t)slot >= ctx->slots.size()) return VS_EINVAL;
+    Slot &s = ctx->slots[slot];
+    CU(cudaSetDevice(s.dev));
+    CU(cudaStreamSynchronize(s.compute));
+    if (s.own_compute) CU(cudaStreamDestroy(s.compute));
+    s.compute = (cudaStream_t)cuda_stream;
+    s.own_compute = false;
+    return VS_OK;
+}
+
+int vs_sync(vs_ctx *ctx)
+{
+    if (!ctx) return VS_EINVAL;
+    int status = 0;
+    for (Slot &s : ctx->slots) {
+        CU(cudaSetDevice(s.dev));
+        CU(cudaStreamSynchronize(s.compute));
+        CU(cudaStreamSynchronize(s.copy));
+        if (s.h_status.p && *(int32_t *)s.h_status.p) { status = *(int32_t *)s.h_status.p; *(int32_t *)s.h_status.p = 0; }
+    }
+    if (ctx->timing_pending) {
+        Slot &s = ctx->slots[0];
+        ctx->timing_pending = false;
+        if (s.tev_used >= 2) {
+            /* layout: t_first, then (e0,e1,e2) per slab, then t_last */
+            float ms = 0.0f;
+            for (size_t k = 1; k + 3 <= s.tev_used - 1; k += 3) {
+                if (cudaEventElapsedTime(&ms, s.tev[k], s.tev[k + 1]) == cudaSuccess) ctx->timing.plan_ms += ms;
+                if (cudaEventElapsedTime(&ms, s.tev[k + 1], s.tev[k + 2]) == cudaSuccess) ctx->timing.render_ms += ms;
+            }
+            if (cudaEventElapsedTime(&ms, s.tev[0], s.tev[s.tev_used - 1]) == cudaSuccess) ctx->timing.total_ms = ms;
+            cudaGetLastError();
+        }
+    }
+    if (status) return fail(ctx, status, "a device kernel reported: %s", vs_strerror(status));
+    return VS_OK;
+}
+
+int vs_get_timing(vs_ctx *ctx, vs_timing *out)
+{
+    if (!ctx || !out) return VS_EINVAL;
+    const int rc = vs_sync(ctx);
+    *out = ctx->timing;
+    return rc;
+}
+
+void *vs_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void vs_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int vs_flow_nsamples(const vs_flow_params *p, size_t n, uint64_t *out)
+{
+    if (!out) return VS_EINVAL;
+    for (size_t i = 0; i < n; i++) out[i] = row_nsamples(flow_row(p, i));
+    return VS_OK;
+}
+
+int vs_flow_max_periods(const vs_flow_params *p, size_t n, uint64_t *out)
+{
+    if (!out) return VS_EINVAL;
+    for (size_t i = 0; i < n; i++) {
+        const FlowRow r = flow_row(p, i);
+        if (row_validate(r)) { out[i] = 0; continue; }
+        out[i] = row_max_periods(r, row_nsamples(r), row_P(r));
+    }
+    return VS_OK;
+}
+
+int vs_flow_validate(const vs_flow_params *p, size_t n, size_t *bad)
+{
+    for (size_t i = 0; i < n; i++) {
+        const int rc = row_validate(flow_row(p, i));
+        if (rc) { if (bad) *bad = i; return rc; }
+    }
+    return VS_OK;
+}
+
+int vs_filter_warmup(vs_ctx *ctx, int preset_key, float gain)
+{
+    (void)gain;
+    if (!ctx) return VS_EINVAL;
+    const int k = preset_index(preset_key);
+    return k < 0 ? VS_EPRESET : ctx->warm[k];
+}
+
+int vs_flowgen_batch(vs_ctx *ctx, const vs_flow_params *p, size_t n, int16_t *pcm_out, const uint64_t *offsets, vs_period_log *log)
+{
+    Batch b = {VS_MODE_FLOW, n, p, nullptr, nullptr, nullptr, nullptr, pcm_out, offsets, nullptr, log};
+    return run_batch(ctx, b);
+}
+
+int vs_vowel_filter_batch(vs_ctx *ctx, const int16_t *flow_in, const uint64_t *in_offsets, const uint64_t *nsamp,
+                          const vs_filter_params *f, size_t n, int16_t *pcm_out, const uint64_t *out_offsets, double *raw_out)
+{
+    Batch b = {VS_MODE_FILTER, n, nullptr, f, flow_in, in_offsets, nsamp, pcm_out, out_offsets, raw_out, nullptr};
+    return run_batch(ctx, b);
+}
+
+int vs_synth_batch(vs_ctx *ctx, const vs_flow_params *p, const vs_filter_params *f, size_t n, int16_t *pcm_out,
+                   const uint64_t *offsets, double *raw_out)
+{
+    Batch b = {VS_MODE_SYNTH, n, p, f, nullptr, nullptr, nullptr, pcm_out, offsets, raw_out, nullptr};
+    return run_batch(ctx, b);
+}
+
+} /* extern "C" */

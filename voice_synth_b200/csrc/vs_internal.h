@@ -1,0 +1,83 @@
+/* vs_internal.h -- structures shared by the host side (vs_api.cu) and the kernels (vs_kernels.cu).
+ * Not part of the ABI. */
+#ifndef VS_INTERNAL_H
+#define VS_INTERNAL_H
+#include <stdint.h>
+
+#define VS_ORDER   22          /* vowel_new.c:172 */
+#define VS_RING    24          /* state ring / samples per unrolled filter block (>= VS_ORDER, 3 x 16 B of PCM) */
+#define VS_NT      128         /* threads per CTA of the plan and render kernels */
+#define VS_RNG_DEG 31          /* glibc TYPE_3 */
+
+/* per-stream descriptor, prepared on the host, read once per thread */
+struct VsStream {
+    uint32_t n;            /* samples in the stream, flowgen_shimmer.c:242                        */
+    int32_t  P;            /* nominal period (int)((float)fs/F0), :244                            */
+    int32_t  T2;           /* ceil(0.5*cq*P), :317                                                */
+    uint32_t cos_off;      /* first entry of this T2's cosine table                               */
+    int32_t  amp;
+    float    DC;
+    float    jitter, shimmer, K, Kvar, noise;
+    uint32_t seed;
+    float    gain, pre;
+    int16_t  DCs;          /* (short)DC                                                           */
+    uint8_t  flags;        /* VS_F_*                                                              */
+    uint8_t  preset;       /* index into "aiu1234567"                                             */
+    uint32_t chunk0;       /* id of the stream's first chunk                                      */
+    uint32_t n_chunks;
+    uint32_t tab_cap;      /* period-table capacity                                               */
+    uint32_t pad0;
+    uint64_t out_off;      /* samples, relative to pcm_out (and raw_out)                          */
+    uint64_t in_off;       /* samples, relative to flow_in (filter-only mode)                     */
+    uint64_t tab_off;      /* first entry of the stream's period table                            */
+    uint64_t log_off;      /* first record of the stream's user-facing period log                 */
+};
+
+/* one time-chunk of one stream = one render thread */
+struct VsChunk {
+    uint32_t stream;
+    uint32_t emit_lo, emit_hi;   /* samples [emit_lo, emit_hi) are written by this chunk           */
+    uint32_t gen_target;         /* generation starts at the period containing this sample         */
+    uint32_t first_period;       /* filled by the plan kernel                                      */
+    uint32_t pad[3];
+};
+
+/* period table entry written by the plan kernel, read by the render kernel */
+struct VsPeriod {
+    uint32_t start;        /* first sample of the period                                          */
+    int32_t  T;            /* period length                                                       */
+    float    A;            /* amplitude                                                           */
+    float    Knew;         /* closure speed                                                       */
+    int32_t  T3, T4;       /* closure instant / DC-crossing instant (valid with noise or log)     */
+    int32_t  ndw;          /* NoiseDistWidth                                                      */
+    uint32_t npert;        /* random() draws of the period before its first noise draw            */
+};
+
+/* kernel launch argument blocks */
+struct VsPlanArgs {
+    const VsStream *streams;
+    uint32_t        n_streams;
+    VsChunk        *chunks;
+    VsPeriod       *table;
+    uint32_t       *rng_snap;       /* [n_chunks][32] or NULL                                     */
+    uint32_t       *n_periods;      /* [n_streams]                                                */
+    const double   *costab;
+    void           *log;            /* vs_period_rec* or NULL                                     */
+    int32_t        *status;         /* device error flag                                          */
+    int             need_pulse;     /* evaluate the pulse for every stream (log requested)        */
+};
+
+struct VsRenderArgs {
+    const VsStream *streams;
+    const VsChunk  *chunks;
+    uint32_t        n_chunks;
+    const VsPeriod *table;
+    const uint32_t *rng_snap;
+    const double   *costab;
+    const double   *coef;           /* [10][24] denominators, device copy                         */
+    const int16_t  *flow_in;        /* filter-only mode                                           */
+    int16_t        *pcm_out;
+    double         *raw_out;        /* nullable                                                   */
+};
+
+#endif
