@@ -68,7 +68,7 @@ def test_flowgen_chunked_equals_unchunked(ctx, vs, golden):
     cases, p = _golden_flow_params(golden, vs)
     ref, offs, ns = ctx.flowgen_batch(p)
     for L in (64, 1000, 4096):
-        ctx.set_option(vs.api.OPT_CHUNK_SAMPLES if hasattr(vs, "api") else 1, L)
+        ctx.set_option(vs.OPT_CHUNK_SAMPLES, L)
         out, _, _ = ctx.flowgen_batch(p)
         assert np.array_equal(out, ref), L
     ctx.set_option(1, 0)
