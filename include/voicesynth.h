@@ -132,6 +132,10 @@ const char *vs_last_error(vs_ctx *ctx);
 int         vs_abi_version(void);
 int         vs_device_count(void);
 
+/* DFMA throughput of device slot 0 (8 independent chains/thread, all SMs): the FP64-pipe roofline
+ * denominator.  *sm_mhz_out (nullable) = the SM clock this rate implies at 64 DFMA/clk/SM. */
+int         vs_measure_fp64_peak(vs_ctx *ctx, double *tflops_out, double *sm_mhz_out);
+
 /* pinned host memory for zero-staging transfers */
 void       *vs_host_alloc(size_t bytes);
 void        vs_host_free(void *p);

@@ -5,7 +5,7 @@ import pathlib
 LIB_PATH = pathlib.Path(__file__).resolve().parent / "lib" / "libvoicesynth_cuda.so"
 
 EXPORTS = ["vs_abi_version", "vs_device_count", "vs_strerror", "vs_last_error", "vs_ctx_create", "vs_ctx_destroy",
-           "vs_ctx_set_option", "vs_ctx_set_stream", "vs_sync", "vs_get_timing", "vs_host_alloc", "vs_host_free",
+           "vs_ctx_set_option", "vs_ctx_set_stream", "vs_sync", "vs_get_timing", "vs_measure_fp64_peak", "vs_host_alloc", "vs_host_free",
            "vs_flow_nsamples", "vs_flow_max_periods", "vs_flow_validate", "vs_filter_warmup",
            "vs_flowgen_batch", "vs_vowel_filter_batch", "vs_synth_batch"]
 
@@ -50,6 +50,7 @@ def load():
     L.vs_ctx_set_stream.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.vs_sync.argtypes = [C.c_void_p]
     L.vs_get_timing.argtypes = [C.c_void_p, C.POINTER(TimingC)]
+    L.vs_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.vs_host_alloc.restype = C.c_void_p
     L.vs_host_alloc.argtypes = [C.c_size_t]
     L.vs_host_free.argtypes = [C.c_void_p]

@@ -258,6 +258,11 @@ class Context:
         self._check(self.L.vs_get_timing(self.h, C.byref(t)))
         return {k: getattr(t, k) for k, _ in TimingC._fields_}
 
+    def fp64_peak(self):
+        t, mhz = C.c_double(), C.c_double()
+        self._check(self.L.vs_measure_fp64_peak(self.h, C.byref(t), C.byref(mhz)))
+        return t.value, mhz.value
+
     def filter_warmup(self, preset, gain=10.0):
         return self.L.vs_filter_warmup(self.h, ord(preset), gain)
 

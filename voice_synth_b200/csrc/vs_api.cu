@@ -29,6 +29,7 @@
 enum { VS_MODE_FLOW = 0, VS_MODE_SYNTH = 1, VS_MODE_FILTER = 2 };
 cudaError_t vs_launch_plan(const VsPlanArgs &a, bool want_log, cudaStream_t s);
 cudaError_t vs_launch_render(const VsRenderArgs &a, int mode, bool noise, bool exact, cudaStream_t s);
+cudaError_t vs_launch_fp64_peak(double *scratch, int blocks, int iters, cudaStream_t s);
 
 namespace {
 
@@ -50,8 +51,8 @@ struct Slot {
     cudaEvent_t h2d_done = nullptr;
     cudaEvent_t slab_done[2] = {nullptr, nullptr};   /* D2H of the slab using pcm[k] finished */
     cudaEvent_t slab_ready = nullptr;                /* render of the current slab finished   */
-    DevBuf streams, chunks, table, snap, nper, costab, coef, status, pcm[2], raw[2], flowin[2], log;
-    PinBuf h_streams, h_chunks, h_nper, h_status;
+    DevBuf streams, chunks, order, table, snap, nper, costab, coef, status, pcm[2], raw[2], flowin[2], log;
+    PinBuf h_streams, h_chunks, h_order, h_nper, h_status;
     size_t costab_uploaded = 0;
     std::vector<cudaEvent_t> tev;                    /* timing events (slot 0 only) */
     size_t tev_used = 0;
@@ -70,6 +71,7 @@ struct vs_ctx {
     std::vector<double> cos_host;
     std::map<int, uint32_t> cos_index;
     int warm[VS_NUM_PRESETS];    /* warm-up samples per preset at opt_tol (gain-independent part) */
+    double l1gain[VS_NUM_PRESETS]; /* sum |h[n]| of each preset: |y| <= l1gain * gain * max|x| */
     std::string err;
     vs_timing timing;
     bool timing_pending = false;
@@ -237,9 +239,26 @@ int warmup_for(const double *A, double tol)
     return last + 1;
 }
 
+double l1_gain_for(const double *A)
+{
+    double s[VS_ORDER] = {0.0};
+    double sum = 0.0;
+    for (int n = 0; n < 60000; n++) {
+        double y0 = n == 0 ? 1.0 : 0.0;
+        for (int k = 0; k < VS_ORDER; k++) y0 -= A[k + 1] * s[k];
+        for (int k = VS_ORDER - 1; k > 0; k--) s[k] = s[k - 1];
+        s[0] = y0;
+        sum += std::fabs(y0);
+    }
+    return sum;
+}
+
 void compute_warmups(vs_ctx *ctx)
 {
-    for (int k = 0; k < VS_NUM_PRESETS; k++) ctx->warm[k] = warmup_for(vs_preset_den[k], ctx->opt_tol);
+    for (int k = 0; k < VS_NUM_PRESETS; k++) {
+        ctx->warm[k] = warmup_for(vs_preset_den[k], ctx->opt_tol);
+        ctx->l1gain[k] = l1_gain_for(vs_preset_den[k]);
+    }
 }
 
 uint32_t cos_table_for(vs_ctx *ctx, int T2)
@@ -253,6 +272,13 @@ uint32_t cos_table_for(vs_ctx *ctx, int T2)
         volatile double num = pi * i;                                 /* PI*i/T2 == ((4.0*atan(1.0))*i)/T2 */
         volatile double arg = num / T2;
         ctx->cos_host.push_back(std::cos(arg));
+    }
+    /* h[i] = 0.5*(1-c[i]): (A*0.5)*(1.0-c) == A*h bit for bit, scaling by 0.5 being exact (:319) */
+    for (int i = 0; i < T2; i++) {
+        volatile double om = 1.0 - ctx->cos_host[off + i];
+        volatile double h = 0.5 * om;
+        const double hv = h;
+        ctx->cos_host.push_back(hv);
     }
     ctx->cos_index[T2] = off;
     return off;
@@ -293,8 +319,11 @@ struct Batch {
     vs_period_log *log;
 };
 
-/* Choose the time-chunk length for a group of streams (SURVEY.md 7 "Occupancy"): enough chunks to
- * give every SM sub-partition `opt_warps` warps, but never shorter than the carry warm-up costs. */
+/* Choose the time-chunk length for a group of streams (SURVEY.md 7 "Occupancy").
+ * Filtering modes: the FP64 pipe of an SM sub-partition is saturated by ONE consumer warp, so the
+ * kernel time is  waves * (L + warm-up)  sample-steps with  waves = ceil(warps / (SMs*4));  every
+ * chunk but the first pays the warm-up again.  Pick the chunk count per stream that minimises it.
+ * Flow mode has no carry, chunks are free: aim at `8*opt_warps` warps per sub-partition. */
 uint32_t choose_chunk(vs_ctx *ctx, const Slot &slot, int mode, size_t n_streams, uint64_t total, double avg_warm)
 {
     if (ctx->opt_chunk < 0) return 0;
@@ -304,14 +333,26 @@ uint32_t choose_chunk(vs_ctx *ctx, const Slot &slot, int mode, size_t n_streams,
         L = (L + 7u) & ~7u;
         return L < 64 ? 64 : L;
     }
-    const double want_threads = (double)slot.sm_count * 4.0 * 32.0 * ctx->opt_warps;
-    if ((double)n_streams >= want_threads) return 0;
-    double L = std::ceil((double)total / want_threads);
-    /* with a filter, every chunk but the first pays avg_warm extra samples: do not go below it */
-    const double floor_len = (mode == VS_MODE_FLOW) ? 1024.0 : std::max(2048.0, 1.5 * avg_warm);
-    if (L < floor_len) L = floor_len;
-    uint32_t Li = ((uint32_t)L + 7u) & ~7u;
-    return Li;
+    const double smsp = (double)slot.sm_count * 4.0;
+    const double avg_n = (double)total / (double)n_streams;
+    if (mode == VS_MODE_FLOW) {
+        const double want_threads = smsp * 32.0 * 8.0 * ctx->opt_warps;
+        if ((double)n_streams >= want_threads) return 0;
+        double L = std::ceil((double)total / want_threads);
+        if (L < 1024.0) L = 1024.0;
+        return ((uint32_t)L + 7u) & ~7u;
+    }
+    double best_cost = 1e300;
+    uint32_t best_L = 0;
+    for (int C = 1; C <= 256; C++) {
+        const double L = std::ceil(avg_n / C / 8.0) * 8.0;
+        if (C > 1 && L < 512.0) break;
+        const double warps = std::ceil((double)n_streams * C / 32.0);
+        const double waves = std::ceil(warps / smsp);
+        const double cost = waves * (L + (C > 1 ? avg_warm : 0.0));
+        if (cost < best_cost * 0.999) { best_cost = cost; best_L = C == 1 ? 0u : (uint32_t)L; }
+    }
+    return best_L;
 }
 
 int run_batch(vs_ctx *ctx, const Batch &b)
@@ -327,7 +368,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
     /* ---- 1. per-stream descriptors ---------------------------------------------------------- */
     std::vector<VsStream> hs(n);
     uint64_t max_n = 0;
-    bool any_noise = false;
+    bool any_noise = false, checked_quant = false;
     for (size_t i = 0; i < n; i++) {
         VsStream &s = hs[i];
         memset(&s, 0, sizeof s);
@@ -356,6 +397,8 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             s.gain = b.ff && b.ff->gain ? b.ff->gain[i] : 10.0f;
             s.pre = b.ff && b.ff->pre ? b.ff->pre[i] : 1.0f;
             if (!std::isfinite(s.gain) || !std::isfinite(s.pre)) return fail(ctx, VS_ERANGE, "stream %zu: gain/pre not finite", i);
+            /* worst-case |waveform|: the unchecked quantiser needs it below 2^30 */
+            if (std::fabs((double)s.gain) * (1.0 + std::fabs((double)s.pre)) * 32768.0 * ctx->l1gain[pi] >= 536870912.0) checked_quant = true;
         }
         max_n = std::max<uint64_t>(max_n, s.n);
     }
@@ -460,6 +503,14 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         }
         slab_c0[n_slabs] = hc.size();
         const size_t nc = hc.size();
+        /* render order: longest chunks first inside each slab, so that the 32 lanes of a warp run
+         * windows of similar count and the tail of the grid is made of short chunks */
+        std::vector<uint32_t> order(nc);
+        for (size_t c = 0; c < nc; c++) order[c] = (uint32_t)c;
+        for (size_t k = 0; k < n_slabs; k++)
+            std::stable_sort(order.begin() + slab_c0[k], order.begin() + slab_c0[k + 1], [&](uint32_t x, uint32_t y) {
+                return hc[x].emit_hi - hc[x].gen_target > hc[y].emit_hi - hc[y].gen_target;
+            });
         ctx->timing.chunks += (uint32_t)nc;
         ctx->timing.samples += total;
         ctx->timing.warmup_samples += warm_total;
@@ -468,6 +519,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         int rc;
         if ((rc = dev_reserve(ctx, sl, sl.streams, ns * sizeof(VsStream)))) return rc;
         if ((rc = dev_reserve(ctx, sl, sl.chunks, nc * sizeof(VsChunk)))) return rc;
+        if ((rc = dev_reserve(ctx, sl, sl.order, nc * sizeof(uint32_t)))) return rc;
         if ((rc = dev_reserve(ctx, sl, sl.nper, ns * sizeof(uint32_t)))) return rc;
         if ((rc = dev_reserve(ctx, sl, sl.status, sizeof(int32_t)))) return rc;
         if (b.mode != VS_MODE_FILTER) {
@@ -483,6 +535,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         }
         if ((rc = pin_reserve(ctx, sl.h_streams, ns * sizeof(VsStream)))) return rc;
         if ((rc = pin_reserve(ctx, sl.h_chunks, nc * sizeof(VsChunk)))) return rc;
+        if ((rc = pin_reserve(ctx, sl.h_order, nc * sizeof(uint32_t)))) return rc;
         if ((rc = pin_reserve(ctx, sl.h_nper, ns * sizeof(uint32_t)))) return rc;
         if ((rc = pin_reserve(ctx, sl.h_status, sizeof(int32_t)))) return rc;
 
@@ -542,9 +595,11 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             }
         }
         memcpy(sl.h_chunks.p, hc.data(), nc * sizeof(VsChunk));
+        memcpy(sl.h_order.p, order.data(), nc * sizeof(uint32_t));
         *(int32_t *)sl.h_status.p = 0;
         CU(cudaMemcpyAsync(sl.streams.p, sl.h_streams.p, ns * sizeof(VsStream), cudaMemcpyHostToDevice, sl.compute));
         CU(cudaMemcpyAsync(sl.chunks.p, sl.h_chunks.p, nc * sizeof(VsChunk), cudaMemcpyHostToDevice, sl.compute));
+        CU(cudaMemcpyAsync(sl.order.p, sl.h_order.p, nc * sizeof(uint32_t), cudaMemcpyHostToDevice, sl.compute));
         CU(cudaMemsetAsync(sl.status.p, 0, sizeof(int32_t), sl.compute));
 
         cudaEvent_t t_first = nullptr;
@@ -593,15 +648,17 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             VsRenderArgs ra;
             memset(&ra, 0, sizeof ra);
             ra.streams = (const VsStream *)sl.streams.p;
-            ra.chunks = (const VsChunk *)sl.chunks.p + c0;
+            ra.chunks = (const VsChunk *)sl.chunks.p;
+            ra.order = (const uint32_t *)sl.order.p + c0;
             ra.n_chunks = (uint32_t)(c1 - c0);
             ra.table = (const VsPeriod *)sl.table.p;
-            ra.rng_snap = any_noise ? (const uint32_t *)sl.snap.p + c0 * 32 : nullptr;
+            ra.rng_snap = any_noise ? (const uint32_t *)sl.snap.p : nullptr;
             ra.costab = (const double *)sl.costab.p;
             ra.coef = (const double *)sl.coef.p;
             ra.flow_in = d_in;
             ra.pcm_out = d_pcm;
             ra.raw_out = d_raw;
+            ra.checked_quant = checked_quant ? 1 : 0;
             CU(vs_launch_render(ra, b.mode, any_noise, exact, sl.compute));
             ctx->timing.launches++;
             if (g == 0) CU(cudaEventRecord(e2, sl.compute));
@@ -737,10 +794,10 @@ void vs_ctx_destroy(vs_ctx *ctx)
         cudaSetDevice(s.dev);
         if (s.compute) cudaStreamSynchronize(s.compute);
         if (s.copy) cudaStreamSynchronize(s.copy);
-        DevBuf *bufs[] = {&s.streams, &s.chunks, &s.table, &s.snap, &s.nper, &s.costab, &s.coef, &s.status,
+        DevBuf *bufs[] = {&s.streams, &s.chunks, &s.order, &s.table, &s.snap, &s.nper, &s.costab, &s.coef, &s.status,
                           &s.pcm[0], &s.pcm[1], &s.raw[0], &s.raw[1], &s.flowin[0], &s.flowin[1], &s.log};
         for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
-        PinBuf *pins[] = {&s.h_streams, &s.h_chunks, &s.h_nper, &s.h_status};
+        PinBuf *pins[] = {&s.h_streams, &s.h_chunks, &s.h_order, &s.h_nper, &s.h_status};
         for (PinBuf *b : pins) if (b->p) cudaFreeHost(b->p);
         for (cudaEvent_t e : s.tev) cudaEventDestroy(e);
         if (s.h2d_done) cudaEventDestroy(s.h2d_done);
@@ -825,6 +882,34 @@ void *vs_host_alloc(size_t bytes)
     return p;
 }
 void vs_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int vs_measure_fp64_peak(vs_ctx *ctx, double *tflops_out, double *sm_mhz_out)
+{
+    if (!ctx || !tflops_out) return VS_EINVAL;
+    Slot &s = ctx->slots[0];
+    CU(cudaSetDevice(s.dev));
+    const int blocks = s.sm_count * 8, iters = 1 << 16;
+    double *scratch = nullptr;
+    CU(cudaMalloc(&scratch, (size_t)blocks * 256 * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CU(cudaEventRecord(e0, s.compute));
+        CU(vs_launch_fp64_peak(scratch, blocks, iters, s.compute));
+        CU(cudaEventRecord(e1, s.compute));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(scratch);
+    const double fma = (double)blocks * 256.0 * 8.0 * (double)iters;
+    *tflops_out = 2.0 * fma / ((double)best * 1e-3) / 1e12;
+    if (sm_mhz_out) *sm_mhz_out = fma / ((double)best * 1e-3) / ((double)s.sm_count * 64.0) / 1e6;  /* if 64 DFMA/clk/SM */
+    return VS_OK;
+}
 
 int vs_flow_nsamples(const vs_flow_params *p, size_t n, uint64_t *out)
 {

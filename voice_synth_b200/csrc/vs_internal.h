@@ -8,6 +8,8 @@
 #define VS_RING    24          /* state ring / samples per unrolled filter block (>= VS_ORDER, 3 x 16 B of PCM) */
 #define VS_NT      128         /* threads per CTA of the plan and render kernels */
 #define VS_RNG_DEG 31          /* glibc TYPE_3 */
+#define VS_WIN     192         /* samples per stream per render window (8 ring blocks, 24 x 16 B)  */
+#define VS_TS      194         /* tile row stride in int16: 97 words, odd => conflict-free columns  */
 
 /* per-stream descriptor, prepared on the host, read once per thread */
 struct VsStream {
@@ -42,15 +44,15 @@ struct VsChunk {
     uint32_t pad[3];
 };
 
-/* period table entry written by the plan kernel, read by the render kernel */
+/* period table entry (32 B) written by the plan kernel, read by the render kernel */
 struct VsPeriod {
+    double   Ad;           /* (double)Amplitude                                                   */
+    double   Kd;           /* (double)Knew                                                        */
     uint32_t start;        /* first sample of the period                                          */
-    int32_t  T;            /* period length                                                       */
-    float    A;            /* amplitude                                                           */
-    float    Knew;         /* closure speed                                                       */
-    int32_t  T3, T4;       /* closure instant / DC-crossing instant (valid with noise or log)     */
+    uint32_t T_np;         /* period length T (low 16 bits) | random() draws of the period before
+                              its first noise draw (high 16 bits)                                 */
+    uint32_t T34;          /* T3 (low 16) | T4 (high 16): closure / DC-crossing instants (noise)  */
     int32_t  ndw;          /* NoiseDistWidth                                                      */
-    uint32_t npert;        /* random() draws of the period before its first noise draw            */
 };
 
 /* kernel launch argument blocks */
@@ -70,6 +72,7 @@ struct VsPlanArgs {
 struct VsRenderArgs {
     const VsStream *streams;
     const VsChunk  *chunks;
+    const uint32_t *order;          /* render thread t works on chunk order[t] (sorted by length)   */
     uint32_t        n_chunks;
     const VsPeriod *table;
     const uint32_t *rng_snap;
@@ -78,6 +81,7 @@ struct VsRenderArgs {
     const int16_t  *flow_in;        /* filter-only mode                                           */
     int16_t        *pcm_out;
     double         *raw_out;        /* nullable                                                   */
+    int             checked_quant;  /* 1: |waveform| may reach 2^30, use the range-checked quantiser */
 };
 
 #endif

@@ -5,11 +5,20 @@
  *                     random walks with their rejection loops, the closure-speed draw, and (with
  *                     -n) the pulse power and the number of noise draws.  Emits a period table and,
  *                     per time-chunk, the period the chunk starts in plus the RNG state there.
- *   vs_render_kernel  one thread per (stream, time-chunk), lock-step over samples: pulse samples
- *                     from the period table + host-libm cosine tables, closed-phase noise, and
- *                     (fused / filter modes) the order-22 FP64 all-pole recurrence of
- *                     vowel_new.c:252-296 with its round-half-down quantiser, state kept in a
- *                     24-entry register ring so that one unrolled block yields 3 x 16-byte stores.
+ *
+ *   vs_render_kernel  one LANE per (stream, time-chunk), one WARP per 32 of them, no block-level
+ *                     synchronisation.  Per window of 96 samples the warp runs three phases over a
+ *                     private shared-memory tile [32 rows][96 int16]:
+ *                       G  generate: for each row in turn the 32 lanes evaluate 32 consecutive
+ *                          samples of that stream.  Given the period table a sample is a pure
+ *                          function of its index (flowgen_shimmer.c:319,328,335), so this phase is
+ *                          divergence-free and closed-phase groups cost nothing.
+ *                       F  filter: each lane runs the order-22 FP64 all-pole recurrence
+ *                          (vowel_new.c:266-289) down its own row, in place.  The state is a
+ *                          24-entry register ring, fully unrolled: ~25 FP64-pipe instructions per
+ *                          sample with 22 independent products -> the FP64 pipe is the bound.
+ *                       W  write: the warp stores the rows as whole 16-byte pieces, consecutive
+ *                          lanes on consecutive pieces of a row (full 32-byte sectors).
  *
  * Every operation that decides an integer (period length, amplitude, sample value, draw count) is
  * written with explicit round-to-nearest intrinsics in the reference's evaluation order, so those
@@ -22,6 +31,7 @@
 #include "vs_internal.h"
 
 #define VS_RAND_MAX_D 2147483647.0
+#define VS_FULL 0xffffffffu
 
 /* ------------------------------------------------------------------------------------------------
  * conversions with x86-64 semantics (cvttsd2si: out-of-range -> 0x80000000, then keep low 16 bits)
@@ -35,6 +45,24 @@ __device__ __forceinline__ int16_t vs_d2s(double v)
 {
     return (int16_t)(uint16_t)(uint32_t)vs_d2i(v);
 }
+/* (short)ceil(v) for |v| < 2^31 (every pulse/noise value: |v| <= 1.8*32767 resp. NDW): one F2I */
+__device__ __forceinline__ int vs_ceil_s16(double v)
+{
+    return (int)(int16_t)(uint16_t)(uint32_t)__double2int_ru(v);
+}
+
+/* r / d for a CONSTANT d with the reciprocal-multiply + FMA-residual sequence.  Exact (== IEEE
+ * division) for every r in [0, 2^31) and both constants used here: checked exhaustively by
+ * tests/tools/divcheck.c. */
+__device__ __forceinline__ double vs_div_const(double r, double d, double inv)
+{
+    const double q0 = __dmul_rn(r, inv);
+    const double rem = __fma_rn(-q0, d, r);
+    return __fma_rn(rem, inv, q0);
+}
+#define VS_INV_RM  (1.0 / 2147483647.0)
+#define VS_RM4     (2147483647.0 * 10000.0)
+#define VS_INV_RM4 (1.0 / (2147483647.0 * 10000.0))
 
 /* ------------------------------------------------------------------------------------------------
  * glibc random() TYPE_3 (r[i] = r[i-3] + r[i-31], output >> 1).  State lives in shared memory,
@@ -85,25 +113,28 @@ __device__ void vs_rng_load(VsRng &g, const uint32_t *src)
 
 /* ------------------------------------------------------------------------------------------------
  * pulse samples (flowgen_shimmer.c:319, :328) and the noise sample (:387, :394, :591-600)
+ *   rising : ceil((A*0.5)*(1-c)) == ceil(A*h) with h = 0.5*(1-c) tabulated (scaling by 0.5 is exact)
+ *   falling: ceil(A*((K*c - K) + 1.0))
  * ---------------------------------------------------------------------------------------------- */
-__device__ __forceinline__ int16_t vs_rising(double Ah, double c)
+__device__ __forceinline__ int vs_rising(double Ad, double h)
 {
-    return vs_d2s(ceil(__dmul_rn(Ah, __dsub_rn(1.0, c))));
+    return vs_ceil_s16(__dmul_rn(Ad, h));
 }
-__device__ __forceinline__ int16_t vs_falling(double Ad, double Kd, double c)
+__device__ __forceinline__ int vs_falling(double Ad, double Kd, double c)
 {
-    return vs_d2s(ceil(__dmul_rn(Ad, __dadd_rn(__dsub_rn(__dmul_rn(Kd, c), Kd), 1.0))));
+    return vs_ceil_s16(__dmul_rn(Ad, __dadd_rn(__dsub_rn(__dmul_rn(Kd, c), Kd), 1.0)));
 }
-__device__ __forceinline__ int16_t vs_noise_w(int32_t r, int32_t ndw)
+__device__ __forceinline__ int vs_noise_w(int32_t r, int32_t ndw)
 {
-    const double u = __ddiv_rn((double)r, VS_RAND_MAX_D);
-    return vs_d2s(ceil(__dsub_rn(__dmul_rn(u, (double)ndw), __ddiv_rn((double)ndw, 2.0))));
+    const double u = vs_div_const((double)r, VS_RAND_MAX_D, VS_INV_RM);
+    const double nd = (double)ndw;
+    return vs_ceil_s16(__dsub_rn(__dmul_rn(u, nd), __dmul_rn(nd, 0.5)));
 }
-__device__ __forceinline__ int16_t vs_clip_ceil(float v)
+/* truncate((float)x + w): both are 16-bit integers, so the float sum is exact and ceil is a no-op */
+__device__ __forceinline__ int vs_add_clip(int x, int w)
 {
-    if (v > 32767.0f) return 32767;
-    if (v < -32767.0f) return -32767;
-    return vs_d2s(ceil((double)v));
+    const int s = x + w;
+    return s > 32767 ? 32767 : (s < -32767 ? -32767 : s);
 }
 
 /* ================================================================================================
@@ -129,31 +160,36 @@ __global__ void __launch_bounds__(VS_NT) vs_plan_kernel(const VsPlanArgs a)
     const float t_hi = __fmul_rn(1.2f, Pf), t_lo = __fmul_rn(0.8f, Pf);
     const float a_hi = __fmul_rn(1.8f, ampf), a_lo = __fmul_rn(0.2f, ampf);
     const double jit = (double)st.jitter, shm = (double)st.shimmer;
-    const double *ct = a.costab + st.cos_off;
-    const float DC = st.DC;
-    const int16_t DCs = st.DCs;
+    const double jit2 = __dmul_rn(2.0, jit), shm2 = __dmul_rn(2.0, shm);
+    const double P2 = __dmul_rn(2.0, (double)P), amp2 = __dmul_rn(2.0, (double)st.amp);
+    const double Kbase = (double)st.K, kv2 = (double)__fmul_rn(2.0f, st.Kvar);
+    const double *ct = a.costab + st.cos_off;      /* c[0..T2), then h[0..T2) = 0.5*(1-c) */
+    const double *ht = ct + T2;
+    const int DCi = (int)ceilf(st.DC);             /* (float)x < DC  <=>  x < ceil(DC) for integer x */
+    const int DCs = st.DCs;
 
     int T = P, T4 = 0, ndw = 0;
     float dper = 0.0f, dsh = 0.0f;
     uint32_t count = 0, np = 0, next_c = 0;
     VsPeriod *tab = a.table + st.tab_off;
     VsChunk *chunks = a.chunks + st.chunk0;
+    uint32_t next_target = st.n_chunks ? chunks[0].gen_target : 0xffffffffu;
     vs_period_rec *log = LOG ? (vs_period_rec *)a.log + st.log_off : nullptr;
     int guard = 0;
 
     do {
         uint32_t nd = 0;
         if (do_jit) {                                                     /* :276-290 */
-            const float prev = dper;
+            const double prev = (double)dper;
             float cur;
             do {
                 const int32_t r = vs_rng_next(g); nd++;
-                double t = __ddiv_rn((double)r, VS_RAND_MAX_D * 10000.0);
+                double t = vs_div_const((double)r, VS_RM4, VS_INV_RM4);
                 t = __dmul_rn(__dmul_rn(t, 40000.0), jit);
-                const float J = __double2float_rn(__dsub_rn(t, __dmul_rn(2.0, jit)));
-                const double den = __dsub_rn(2.0, (double)J);
-                const double q1 = __ddiv_rn(__dmul_rn((double)prev, __dadd_rn(2.0, (double)J)), den);
-                const double q2 = __ddiv_rn(__dmul_rn(__dmul_rn(2.0, (double)P), (double)J), den);
+                const double J = (double)__double2float_rn(__dsub_rn(t, jit2));
+                const double den = __dsub_rn(2.0, J);
+                const double q1 = __ddiv_rn(__dmul_rn(prev, __dadd_rn(2.0, J)), den);
+                const double q2 = __ddiv_rn(__dmul_rn(P2, J), den);
                 cur = __double2float_rn(__dadd_rn(q1, q2));
                 T = (int)vs_d2s(ceil((double)__fadd_rn(Pf, cur)));
                 if (++guard > (1 << 22)) { atomicExch(a.status, VS_ERANGE); return; }
@@ -162,50 +198,51 @@ __global__ void __launch_bounds__(VS_NT) vs_plan_kernel(const VsPlanArgs a)
         }
         float A = ampf, S = 0.0f;
         if (do_shm) {                                                     /* :296-306 */
-            const float prev = dsh;
+            const double prev = (double)dsh;
             float cur;
             do {
                 const int32_t r = vs_rng_next(g); nd++;
-                const float eps = __fdiv_rn((float)r, 2147483648.0f);     /* (float)RAND_MAX == 2^31 */
-                S = __double2float_rn(__dsub_rn(__dmul_rn(__dmul_rn((double)eps, 4.0), shm), __dmul_rn(2.0, shm)));
+                const float eps = __fmul_rn((float)r, 4.656612873077393e-10f);   /* / (float)RAND_MAX == * 2^-31, exact */
+                S = __double2float_rn(__dsub_rn(__dmul_rn(__dmul_rn((double)eps, 4.0), shm), shm2));
                 const double den = __dsub_rn(2.0, (double)S);
-                const double q1 = __ddiv_rn(__dmul_rn((double)prev, __dadd_rn(2.0, (double)S)), den);
-                const double q2 = __ddiv_rn(__dmul_rn(__dmul_rn(2.0, (double)st.amp), (double)S), den);
+                const double q1 = __ddiv_rn(__dmul_rn(prev, __dadd_rn(2.0, (double)S)), den);
+                const double q2 = __ddiv_rn(__dmul_rn(amp2, (double)S), den);
                 cur = __double2float_rn(__dadd_rn(q1, q2));
                 A = __fadd_rn(ampf, cur);
                 if (++guard > (1 << 22)) { atomicExch(a.status, VS_ERANGE); return; }
             } while (A > a_hi || A < a_lo);
             dsh = cur;
         }
-        if (T < 1) { atomicExch(a.status, VS_ERANGE); return; }
+        if (T < 1 || T > 32767) { atomicExch(a.status, VS_ERANGE); return; }
 
         /* closure-speed draw, always consumed (:325) */
         const int32_t rk = vs_rng_next(g); nd++;
-        const double kq = __dsub_rn(__ddiv_rn((double)rk, VS_RAND_MAX_D), 0.5);
-        const float Knew = __double2float_rn(
-            __dmul_rn((double)st.K, __dadd_rn(1.0, __dmul_rn((double)__fmul_rn(2.0f, st.Kvar), kq))));
+        const double kq = __dsub_rn(vs_div_const((double)rk, VS_RAND_MAX_D, VS_INV_RM), 0.5);
+        const float Knew = __double2float_rn(__dmul_rn(Kbase, __dadd_rn(1.0, __dmul_rn(kv2, kq))));
 
         /* chunks whose generation starts inside this period: remember where we are */
-        while (next_c < st.n_chunks && chunks[next_c].gen_target < count + (uint32_t)T) {
+        while (next_target < count + (uint32_t)T) {
             chunks[next_c].first_period = np;
             if (noise && a.rng_snap) vs_rng_save(g, a.rng_snap + (size_t)(st.chunk0 + next_c) * 32);
             next_c++;
+            next_target = next_c < st.n_chunks ? chunks[next_c].gen_target : 0xffffffffu;
         }
 
         int T3 = 2 * T2;
         float x_pow = 0.0f, w_pow = 0.0f;
+        uint32_t n_noise = 0;
         if (pulse) {
             /* one pass over the open phase: T4 = last rising index below DC (:320-323), T3 = first
              * falling index below DC (:329), and the float power sum over [T4,T3) in index order
              * (:374-378).  The sum restarts whenever T4 moves; if T4 never moves in this period the
              * sum that started at the stale T4 is the one the reference computes. */
-            const double Ad = (double)A, Ah = __dmul_rn(Ad, 0.5), Kd = (double)Knew;
+            const double Ad = (double)A, Kd = (double)Knew;
             float aux_new = 0.0f, aux_old = 0.0f;
             bool moved = false;
             const int T4_old = T4;
             for (int i = 0; i < T2; i++) {
-                int16_t x = vs_rising(Ah, __ldg(ct + i));
-                if ((float)x < DC) { x = DCs; T4 = i; moved = true; aux_new = 0.0f; }
+                int x = vs_rising(Ad, __ldg(ht + i));
+                if (x < DCi) { x = DCs; T4 = i; moved = true; aux_new = 0.0f; }
                 const float sq = __fmul_rn((float)x, (float)x);
                 if (moved) aux_new = __fadd_rn(aux_new, sq);
                 else if (i >= T4_old) aux_old = __fadd_rn(aux_old, sq);
@@ -213,8 +250,8 @@ __global__ void __launch_bounds__(VS_NT) vs_plan_kernel(const VsPlanArgs a)
             float aux = moved ? aux_new : aux_old;
             int i;
             for (i = T2; i < 2 * T2; i++) {
-                const int16_t x = vs_falling(Ad, Kd, __ldg(ct + i - T2));
-                if ((float)x < DC) break;
+                const int x = vs_falling(Ad, Kd, __ldg(ct + i - T2));
+                if (x < DCi) break;
                 aux = __fadd_rn(aux, __fmul_rn((float)x, (float)x));
             }
             T3 = i;
@@ -223,30 +260,34 @@ __global__ void __launch_bounds__(VS_NT) vs_plan_kernel(const VsPlanArgs a)
                 x_pow = __fdiv_rn(aux, span);
                 const float ax = __double2float_rn(__dadd_rn(1.0, (double)__fdiv_rn(span, (float)T)));
                 ndw = vs_d2i(sqrt((double)__fdiv_rn(__fmul_rn(__fmul_rn(12.0f, ax), x_pow), st.noise)));
-                const int n1 = T4, n2 = T > T3 ? T - T3 : 0;
+                n_noise = (uint32_t)(T4 + (T > T3 ? T - T3 : 0));
                 if (LOG) {
                     float wa = 0.0f;
-                    for (int k = 0; k < n1 + n2; k++) {
-                        const int16_t w = vs_noise_w(vs_rng_next(g), ndw);
+                    for (uint32_t k = 0; k < n_noise; k++) {
+                        const int w = vs_noise_w(vs_rng_next(g), ndw);
                         wa = __fadd_rn(wa, __fmul_rn((float)w, (float)w));
                     }
                     w_pow = __fdiv_rn(wa, (float)T);
                 } else {
-                    for (int k = 0; k < n1 + n2; k++) (void)vs_rng_next(g);
+                    for (uint32_t k = 0; k < n_noise; k++) (void)vs_rng_next(g);
                 }
-                nd += (uint32_t)(n1 + n2);
             }
         }
 
-        if (np >= st.tab_cap) { atomicExch(a.status, VS_ENOMEM); return; }
+        if (np >= st.tab_cap || nd > 65535u || T3 > 65535 || T4 > 65535) {
+            atomicExch(a.status, np >= st.tab_cap ? VS_ENOMEM : VS_ERANGE);
+            return;
+        }
         VsPeriod e;
-        e.start = count; e.T = T; e.A = A; e.Knew = Knew; e.T3 = T3; e.T4 = T4; e.ndw = ndw;
-        e.npert = noise ? nd - (uint32_t)(T4 + (T > T3 ? T - T3 : 0)) : nd;
+        e.Ad = (double)A; e.Kd = (double)Knew; e.start = count;
+        e.T_np = (uint32_t)T | (nd << 16);
+        e.T34 = (uint32_t)T3 | ((uint32_t)T4 << 16);
+        e.ndw = ndw;
         tab[np] = e;
         if (LOG) {
             vs_period_rec r;
             r.T = T; r.T2 = T2; r.T3 = T3; r.T4 = T4; r.A = A; r.Knew = Knew; r.S = S;
-            r.ndraws = (int32_t)nd; r.ndw = ndw; r.x_pow = x_pow; r.w_pow = w_pow; r.reserved = 0;
+            r.ndraws = (int32_t)(nd + n_noise); r.ndw = ndw; r.x_pow = x_pow; r.w_pow = w_pow; r.reserved = 0;
             r.start = count;
             log[np] = r;
         }
@@ -257,185 +298,400 @@ __global__ void __launch_bounds__(VS_NT) vs_plan_kernel(const VsPlanArgs a)
 }
 
 /* ================================================================================================
- * RENDER: one thread per (stream, chunk)
+ * RENDER: one lane per (stream, chunk), one warp per 32 of them
  * ============================================================================================== */
 enum { VS_MODE_FLOW = 0, VS_MODE_SYNTH = 1, VS_MODE_FILTER = 2 };
 
-template <bool NOISE>
-struct VsFlowGen {
+/* what the other lanes need to know about a lane's chunk; lives in shared memory */
+struct __align__(16) VsLane {
     const VsPeriod *tab;
-    const double *ct;
-    uint32_t pidx;
-    int i, T, T2, T3, T4, ndw;
-    bool closed, noise;
-    double Ah, Ad, Kd;
-    float DC;
-    int16_t DCs;
-    VsRng g;
-
-    __device__ __forceinline__ void load_period(bool skip_pert)
-    {
-        const int4 *q = reinterpret_cast<const int4 *>(tab + pidx);
-        const int4 lo = __ldg(q), hi = __ldg(q + 1);
-        T = lo.y;
-        Ad = (double)__int_as_float(lo.z);
-        Ah = __dmul_rn(Ad, 0.5);
-        Kd = (double)__int_as_float(lo.w);
-        T3 = hi.x; T4 = hi.y; ndw = hi.z;
-        i = 0; closed = false;
-        if (NOISE && noise && skip_pert)
-            for (uint32_t k = 0; k < (uint32_t)hi.w; k++) (void)vs_rng_next(g);
-    }
-
-    __device__ __forceinline__ int16_t next()
-    {
-        while (i >= T) { pidx++; load_period(true); }
-        int16_t x;
-        if (i < T2) {                                                     /* :318-324 */
-            x = vs_rising(Ah, __ldg(ct + i));
-            if ((float)x < DC) x = DCs;
-        } else if (!closed && i < 2 * T2) {                               /* :327-330 */
-            x = vs_falling(Ad, Kd, __ldg(ct + i - T2));
-            if ((float)x < DC) { closed = true; x = DCs; }
-        } else {
-            x = DCs;                                                      /* :334-336 */
-        }
-        if (NOISE && noise && (i < T4 || i >= T3)) {                      /* :385-406 */
-            const int16_t w = vs_noise_w(vs_rng_next(g), ndw);
-            x = vs_clip_ceil(__fadd_rn((float)x, (float)w));
-        }
-        i++;
-        return x;
-    }
+    const double *ct;        /* c[0..T2), h[0..T2) */
+    int16_t *orow;
+    const int16_t *fin;
+    int32_t nstart, lo, hi, blk0;
+    int32_t T2, DCi, DCs, noise;
 };
 
-/* vowel_new.c:413-427, literally */
-__device__ __forceinline__ int16_t vs_round2int(double v)
+struct VsEnt {               /* a period-table entry in registers */
+    double Ad, Kd;
+    int start, T, T3, T4, ndw, npert;
+};
+
+__device__ __forceinline__ VsEnt vs_load_entry(const VsPeriod *p)
+{
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+    const int4 b = __ldg(reinterpret_cast<const int4 *>(p) + 1);
+    VsEnt e;
+    e.Ad = a.x; e.Kd = a.y;
+    e.start = b.x;
+    e.T = b.y & 0xffff; e.npert = (int)((uint32_t)b.y >> 16);
+    e.T3 = b.z & 0xffff; e.T4 = (int)((uint32_t)b.z >> 16);
+    e.ndw = b.w;
+    return e;
+}
+
+/* vowel_new.c:413-427, literally (exact mode) */
+__device__ __forceinline__ int vs_round2int(double v)
 {
     const double dec = __dsub_rn(v, floor(v));
     if (dec > 0.5) v = __dadd_rn(v, 1.0);
     if (v > 32767.0) v = 32767.0;
     else if (v < -32767.0) v = -32767.0;
-    return vs_d2s(floor(v));
+    return (int)vs_d2s(floor(v));
 }
 
-__device__ __forceinline__ uint32_t vs_pack2(int16_t lo, int16_t hi)
+/* Fast quantiser: round2int(v) == clip(ceil(v - 0.5)) (round half DOWN) except for v within one ulp
+ * below an integer, where the reference's own x+1 rounds up.  One FP64 add in round-up mode with
+ * the magic constant 2^51+2^50-0.5 (ulp there is 0.5) leaves 2*h in the low mantissa word, h the
+ * smallest multiple of 0.5 >= v-0.5; ceil(h) = (2h+1)>>1.  The high word tells when |v| >= 2^30. */
+__device__ __forceinline__ int vs_quant_fast(double v)
 {
-    return (uint32_t)(uint16_t)lo | ((uint32_t)(uint16_t)hi << 16);
+    const double s = __dadd_ru(v, 3377699720527871.5);
+    const int k2 = __double2loint(s);
+    const int hw = __double2hiint(s);
+    int k = (k2 + 1) >> 1;
+    k = max(-32767, min(32767, k));
+    if (hw - 0x43280000 != (k2 >> 31)) k = __double2hiint(v) < 0 ? -32767 : 32767;
+    return k;
 }
 
-template <int MODE, bool NOISE, bool EXACT>
-__global__ void __launch_bounds__(VS_NT) vs_render_kernel(const VsRenderArgs a)
+/* same, for batches whose waveform is bounded below 2^30 (host-side bound on gain * l1 gain of the preset) */
+__device__ __forceinline__ int vs_quant_fast_nocheck(double v)
 {
-    __shared__ int32_t s_x[VS_RING * VS_NT];
-    __shared__ uint32_t s_rng[(NOISE && MODE != VS_MODE_FILTER) ? VS_RNG_DEG * VS_NT : 1];
+    const int k2 = __double2loint(__dadd_ru(v, 3377699720527871.5));
+    return max(-32767, min(32767, (k2 + 1) >> 1));
+}
 
-    const uint32_t c = blockIdx.x * VS_NT + threadIdx.x;
-    if (c >= a.n_chunks) return;
-    const VsChunk ck = a.chunks[c];
-    const VsStream st = a.streams[ck.stream];
-    int32_t *xs = s_x + threadIdx.x;
+/* ---- shared-memory geometry of the render kernel ------------------------------------------------
+ * A CTA serves VS_NP groups of 32 rows (one row = one stream-chunk).  In the filtering modes a group
+ * is worked by one CONSUMER warp (F phase; warps 0..NP-1, one per SM sub-partition) and VS_PW
+ * PRODUCER warps (G and W phases) over two tiles; in flow mode by a single warp doing G then W.   */
+#define VS_NP        4
+#define VS_PW        3
+#define VS_TILE_I16  (32 * VS_TS)
+#define VS_THREADS_PAIRED ((VS_NP + VS_NP * VS_PW) * 32)
 
-    /* ---- flow source ---- */
-    VsFlowGen<NOISE> gen;
-    int64_t nstart;                       /* first sample this thread generates / reads */
-    const int16_t *fin = nullptr;
-    if (MODE == VS_MODE_FILTER) {
-        nstart = ck.gen_target;
-        fin = a.flow_in + st.in_off;
-    } else {
-        gen.tab = a.table + st.tab_off;
-        gen.ct = a.costab + st.cos_off;
-        gen.pidx = ck.first_period;
-        gen.T2 = st.T2; gen.DC = st.DC; gen.DCs = st.DCs;
-        gen.noise = (st.flags & VS_F_NOISE) != 0;
-        gen.g.r = s_rng + (NOISE ? threadIdx.x : 0);
-        gen.g.f = 3;
-        if (NOISE && gen.noise) vs_rng_load(gen.g, a.rng_snap + (size_t)c * 32);
-        gen.load_period(false);           /* the snapshot was taken after this period's K draw */
-        nstart = __ldg(&gen.tab[gen.pidx].start);
-    }
+#define VS_SMEM_TILES (VS_NP * 2 * VS_TILE_I16 * 2)
+#define VS_SMEM_LANES (VS_NP * 32 * (int)sizeof(VsLane))
+#define VS_SMEM_PIDX  (VS_NP * 32 * 4)
+#define VS_SMEM_BASE  (VS_SMEM_TILES + VS_SMEM_LANES + VS_SMEM_PIDX)
+#define VS_SMEM_NOISE ((VS_RNG_DEG * VS_NT + VS_NP * 32 * VS_WIN) * 4)
 
-    /* ---- filter state: 24-entry ring in registers, coefficients in registers ---- */
-    double y[VS_RING];
-    double cf[VS_ORDER + 1];
-    double gaind = 0.0, pred = 0.0;
-    if (MODE != VS_MODE_FLOW) {
-#pragma unroll
-        for (int j = 0; j < VS_RING; j++) y[j] = 0.0;
-#pragma unroll
-        for (int j = 0; j <= VS_ORDER; j++) cf[j] = __ldg(a.coef + st.preset * VS_RING + j);
-        gaind = (double)st.gain;
-        pred = (double)st.pre;
-    }
+__device__ __forceinline__ void vs_named_barrier(int id, int count)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 
-    /* ---- output geometry: blocks of 24 samples anchored on 16-byte boundaries of the row ---- */
-    int16_t *orow = a.pcm_out + st.out_off;
-    double *rrow = a.raw_out ? a.raw_out + st.out_off : nullptr;
-    const int64_t phase = (int64_t)((reinterpret_cast<uintptr_t>(orow) >> 1) & 7);
-    const int64_t lo = ck.emit_lo, hi = ck.emit_hi;
-    int64_t blk = nstart - ((phase + nstart) & 7);
-
-    for (; blk < hi; blk += VS_RING) {
-        /* 1. 24 flow samples -> shared memory (rolled: the generator is a divergent state machine) */
-#pragma unroll 1
-        for (int k = 0; k < VS_RING; k++) {
-            const int64_t m = blk + k;
-            int32_t x = 0;
-            if (m >= nstart && m < hi) x = (MODE == VS_MODE_FILTER) ? (int32_t)__ldg(fin + m) : (int32_t)gen.next();
-            xs[k * VS_NT] = x;
+/* ---- noise: lane = row; draw the row's random() values for window w into dr[sample - window base] -- */
+__device__ __forceinline__ void vs_draw_window(const VsLane &me, int w, VsRng &g, VsEnt &re, uint32_t &rq, int32_t *dr)
+{
+    const int wb = me.blk0 + w * VS_WIN;
+    if (!me.noise || wb >= me.hi) return;
+    const int mlo = max(wb, me.nstart), mhi = min(wb + VS_WIN, me.hi);
+    for (int m = mlo; m < mhi; m++) {
+        int i = m - re.start;
+        while (i >= re.T) {                                   /* next period: its perturbation and K */
+            re = vs_load_entry(me.tab + (++rq));              /* draws come first (:283,:298,:325)   */
+            for (int k = 0; k < re.npert; k++) (void)vs_rng_next(g);
+            i = m - re.start;
         }
+        if (i < re.T4 || i >= re.T3) dr[m - wb] = vs_rng_next(g);            /* :385, :396 */
+    }
+}
 
-        /* 2. recurrence, fully unrolled so that the ring indices are compile-time registers */
-        int16_t q[VS_RING];
+/* ---- G: the warp generates the VS_WIN samples of ONE row for window w ---------------------------------
+ * Given the period table a sample depends only on its index: closed phase = DC (a word fill), rising
+ * and falling branches are contiguous index segments of each period, evaluated 32 samples at a time. */
+template <int MODE, bool NOISE>
+__device__ __forceinline__ void vs_gen_row(int16_t *trow, const VsLane &L, int w, int lane, uint32_t *pidx_slot,
+                                           const int32_t *drow)
+{
+    const int wb = L.blk0 + w * VS_WIN;
+    if (wb >= L.hi) return;
+    const int glo = max(wb, L.nstart), ghi = min(wb + VS_WIN, L.hi);     /* samples that exist */
+
+    if (MODE == VS_MODE_FILTER) {
 #pragma unroll
-        for (int k = 0; k < VS_RING; k++) {
-            const int32_t xi = xs[k * VS_NT];
-            if (MODE == VS_MODE_FLOW) {
-                q[k] = (int16_t)xi;
+        for (int k = lane; k < VS_WIN; k += 32) {
+            const int m = wb + k;
+            trow[k] = (m >= glo && m < ghi) ? __ldg(L.fin + m) : (int16_t)0;
+        }
+        return;
+    }
+
+    /* closed phase everywhere (flowgen_shimmer.c:334-336), zeros outside the stream */
+    if (glo == wb && ghi == wb + VS_WIN) {
+        const uint32_t pat = (uint32_t)(uint16_t)L.DCs * 0x10001u;
+        uint32_t *t32 = reinterpret_cast<uint32_t *>(trow);
+#pragma unroll
+        for (int k = lane; k < VS_WIN / 2; k += 32) t32[k] = pat;
+    } else {
+#pragma unroll
+        for (int k = lane; k < VS_WIN; k += 32) {
+            const int m = wb + k;
+            trow[k] = (m >= glo && m < ghi) ? (int16_t)L.DCs : (int16_t)0;
+        }
+    }
+    __syncwarp();
+
+    const int T2 = L.T2, DCi = L.DCi;
+    const double *ct = L.ct, *ht = L.ct + T2;
+    uint32_t q = *pidx_slot;
+    int pend;
+    for (;;) {
+        const VsEnt e = vs_load_entry(L.tab + q);
+        pend = e.start + e.T;
+        if (pend > glo) {
+            const int rel = e.start - wb;                                 /* tile index of the period's sample 0 */
+            const int a0 = max(0, glo - e.start), a1 = min(e.T, ghi - e.start);       /* in-period index range */
+            /* rising branch (:318-324): i in [0,T2) */
+            for (int i = a0 + lane; i < min(a1, T2); i += 32) {
+                const int v = vs_rising(e.Ad, __ldg(ht + i));
+                if (v >= DCi) trow[rel + i] = (int16_t)v;
+            }
+            /* falling branch (:327-332): i in [T2,2*T2); once below DC it stays below (monotone) */
+            for (int i = max(a0, T2) + lane; i < min(a1, 2 * T2); i += 32) {
+                const int v = vs_falling(e.Ad, e.Kd, __ldg(ct + i - T2));
+                if (v >= DCi) trow[rel + i] = (int16_t)v;
+            }
+            if (NOISE && L.noise) {                                       /* :385-406 */
+                __syncwarp();
+                for (int i = a0 + lane; i < min(a1, e.T4); i += 32)
+                    trow[rel + i] = (int16_t)vs_add_clip(trow[rel + i], vs_noise_w(drow[rel + i], e.ndw));
+                for (int i = max(a0, e.T3) + lane; i < a1; i += 32)
+                    trow[rel + i] = (int16_t)vs_add_clip(trow[rel + i], vs_noise_w(drow[rel + i], e.ndw));
+            }
+        }
+        if (pend >= ghi) break;
+        q++;
+    }
+    if (lane == 0) *pidx_slot = pend > ghi ? q : q + 1;                   /* period holding the next window's first sample */
+}
+
+/* ---- W: one row, whole 16-byte pieces, consecutive lanes on consecutive pieces ----------------------- */
+__device__ __forceinline__ void vs_write_row(const int16_t *trow, const VsLane &L, int w, int lane)
+{
+    const int lo = L.lo, hi = L.hi;
+    const int wb = L.blk0 + w * VS_WIN;
+    if (wb >= hi || wb + VS_WIN <= lo) return;
+    if (lane < VS_WIN / 8) {
+        const int m0 = wb + 8 * lane;
+        if (m0 + 8 > lo && m0 < hi) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(trow) + lane * 4;
+            if (m0 >= lo && m0 + 8 <= hi) {
+                uint4 v;
+                v.x = src[0]; v.y = src[1]; v.z = src[2]; v.w = src[3];
+                *reinterpret_cast<uint4 *>(L.orow + m0) = v;
             } else {
-                double acc = __dmul_rn((double)xi, gaind);                /* vowel_new.c:266-269 */
+                const int16_t *s16 = reinterpret_cast<const int16_t *>(src);
+                for (int k = 0; k < 8; k++)
+                    if (m0 + k >= lo && m0 + k < hi) L.orow[m0 + k] = s16[k];
+            }
+        }
+    }
+}
+
+/* ---- F: one lane, one row, VS_WIN samples of the order-22 recurrence, in place ---------------------- */
+template <bool EXACT, bool RAW, bool CHECKED>
+__device__ __forceinline__ void vs_filter_window(uint32_t *row32, double (&y)[VS_RING], const double (&cf)[VS_ORDER + 1],
+                                                 double gaind, double pred, double *rrow, int wb, int lo, int hi)
+{
+#pragma unroll 1
+    for (int b = 0; b < VS_WIN / VS_RING; b++) {
+        uint32_t *blk32 = row32 + b * (VS_RING / 2);
+#pragma unroll
+        for (int kk = 0; kk < VS_RING / 2; kk++) {
+            const uint32_t pr = blk32[kk];                            /* two int16 flow samples */
+            uint32_t outw = 0;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int k = 2 * kk + h;
+                const int xi = h ? (int)(int16_t)(pr >> 16) : (int)(int16_t)(pr & 0xffffu);
+                double acc = __dmul_rn((double)xi, gaind);            /* vowel_new.c:266-269 */
                 double v;
                 if (EXACT) {
 #pragma unroll
-                    for (int j = 1; j <= VS_ORDER; j++)                   /* :279-281, same order */
+                    for (int j = 1; j <= VS_ORDER; j++)               /* :279-281, same order */
                         acc = __dsub_rn(acc, __dmul_rn(cf[j], y[(k + VS_RING - j) % VS_RING]));
                     v = __dsub_rn(acc, __dmul_rn(pred, y[(k + VS_RING - 1) % VS_RING]));   /* :284 */
                 } else {
 #pragma unroll
-                    for (int j = VS_ORDER; j >= 1; j--)                   /* oldest tap first */
-                        acc = fma(-cf[j], y[(k + VS_RING - j) % VS_RING], acc);
-                    v = fma(-pred, y[(k + VS_RING - 1) % VS_RING], acc);
+                    for (int j = VS_ORDER; j >= 1; j--)               /* oldest tap first */
+                        acc = __fma_rn(-cf[j], y[(k + VS_RING - j) % VS_RING], acc);
+                    v = __fma_rn(-pred, y[(k + VS_RING - 1) % VS_RING], acc);
                 }
-                y[k] = acc;                                               /* :287-289 (ring) */
-                q[k] = vs_round2int(v);
-                if (rrow) {
-                    const int64_t m = blk + k;
+                y[k] = acc;                                           /* :287-289 (ring) */
+                const int qv = EXACT ? vs_round2int(v) : (CHECKED ? vs_quant_fast(v) : vs_quant_fast_nocheck(v));
+                if (RAW) {
+                    const int m = wb + b * VS_RING + k;
                     if (m >= lo && m < hi) rrow[m] = v;
                 }
+                outw |= (uint32_t)(uint16_t)qv << (16 * h);
             }
-        }
-
-        /* 3. three 16-byte pieces; interior pieces are whole by construction */
-#pragma unroll
-        for (int p = 0; p < 3; p++) {
-            const int64_t m0 = blk + 8 * p;
-            if (m0 >= lo && m0 + 8 <= hi) {
-                uint4 w;
-                w.x = vs_pack2(q[8 * p + 0], q[8 * p + 1]);
-                w.y = vs_pack2(q[8 * p + 2], q[8 * p + 3]);
-                w.z = vs_pack2(q[8 * p + 4], q[8 * p + 5]);
-                w.w = vs_pack2(q[8 * p + 6], q[8 * p + 7]);
-                *reinterpret_cast<uint4 *>(orow + m0) = w;
-            } else if (m0 + 8 > lo && m0 < hi) {
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int64_t m = m0 + k;
-                    if (m >= lo && m < hi) orow[m] = q[8 * p + k];
-                }
-            }
+            blk32[kk] = outw;                                         /* in place */
         }
     }
+}
+
+/* FLAGS: bit0 EXACT filter, bit1 RAW output, bit2 CHECKED quantiser */
+template <int MODE, bool NOISE, int FLAGS>
+__global__ void __launch_bounds__(MODE == VS_MODE_FLOW ? VS_NT : VS_THREADS_PAIRED, 1)
+vs_render_kernel(const VsRenderArgs a)
+{
+    constexpr bool PAIRED = MODE != VS_MODE_FLOW;
+    constexpr bool DRAWS = NOISE && MODE != VS_MODE_FILTER;
+    constexpr bool EXACT = (FLAGS & 1) != 0, RAW = (FLAGS & 2) != 0, CHECKED = (FLAGS & 4) != 0;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    int16_t *s_tiles = reinterpret_cast<int16_t *>(s_raw);
+    VsLane *s_lanes = reinterpret_cast<VsLane *>(s_raw + VS_SMEM_TILES);
+    uint32_t *s_pidx = reinterpret_cast<uint32_t *>(s_raw + VS_SMEM_TILES + VS_SMEM_LANES);
+    uint32_t *s_rng = reinterpret_cast<uint32_t *>(s_raw + VS_SMEM_BASE);
+    int32_t *s_draws = reinterpret_cast<int32_t *>(s_raw + VS_SMEM_BASE) + VS_RNG_DEG * VS_NT;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pair = warp % VS_NP;                       /* warps 0..NP-1 consume, NP.. produce */
+    const int prod = PAIRED ? warp / VS_NP - 1 : 0;      /* producer index inside the group, -1 = consumer */
+    const bool consumer = PAIRED && warp < VS_NP;
+    const bool owner = PAIRED ? prod == 0 : true;        /* the warp that sets a group up and owns its RNGs */
+    const uint32_t t = blockIdx.x * VS_NT + pair * 32 + lane;   /* row slot of this lane */
+    const bool active = t < a.n_chunks;
+    int16_t *tile0 = s_tiles + pair * 2 * VS_TILE_I16;
+    VsLane *lanes = s_lanes + pair * 32;
+    uint32_t *pidx = s_pidx + pair * 32;
+    int32_t *draws = s_draws + pair * 32 * VS_WIN;
+    const int group_threads = (1 + VS_PW) * 32;
+
+    /* ---- per-row setup (every warp of the group computes its own copy; the owner publishes it) ----- */
+    uint32_t first_pidx = 0, chunk_id = 0;
+    int preset = 0;
+    double gaind = 0.0, pred = 0.0;
+    double *rrow = nullptr;
+    VsLane me;
+    me.tab = nullptr; me.ct = nullptr; me.orow = nullptr; me.fin = nullptr;
+    me.nstart = 0; me.lo = 0; me.hi = 0; me.blk0 = 0; me.T2 = 0; me.DCi = 0; me.DCs = 0; me.noise = 0;
+    if (active) {
+        chunk_id = a.order ? a.order[t] : t;
+        const VsChunk ck = a.chunks[chunk_id];
+        const VsStream st = a.streams[ck.stream];
+        me.orow = a.pcm_out + st.out_off;
+        me.lo = (int)ck.emit_lo; me.hi = (int)ck.emit_hi;
+        if (MODE == VS_MODE_FILTER) {
+            me.fin = a.flow_in + st.in_off;
+            me.nstart = (int)ck.gen_target;
+        } else {
+            me.tab = a.table + st.tab_off;
+            me.ct = a.costab + st.cos_off;
+            me.T2 = st.T2;
+            me.DCi = (int)ceilf(st.DC);
+            me.DCs = st.DCs;
+            me.noise = (st.flags & VS_F_NOISE) ? 1 : 0;
+            first_pidx = ck.first_period;
+            me.nstart = (int)__ldg(&me.tab[first_pidx].start);
+        }
+        const int phase = (int)((reinterpret_cast<uintptr_t>(me.orow) >> 1) & 7);
+        me.blk0 = me.nstart - ((phase + me.nstart) & 7);
+        preset = st.preset; gaind = (double)st.gain; pred = (double)st.pre;
+        rrow = (RAW && a.raw_out) ? a.raw_out + st.out_off : nullptr;
+    }
+    int nwin = active ? (me.hi - me.blk0 + VS_WIN - 1) / VS_WIN : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nwin = max(nwin, __shfl_xor_sync(VS_FULL, nwin, o));
+    if (owner) { lanes[lane] = me; pidx[lane] = first_pidx; }
+
+    /* noise: the owner warp's lane j owns row j's RNG, restored from the plan kernel's snapshot */
+    VsRng g;
+    g.r = s_rng + (DRAWS ? pair * 32 + lane : 0);
+    g.f = 3;
+    VsEnt re;
+    re.start = 0; re.T = 0x7fffffff; re.T3 = 0; re.T4 = 0; re.npert = 0; re.ndw = 0; re.Ad = re.Kd = 0.0;
+    uint32_t rq = first_pidx;
+    if (DRAWS && owner && active && me.noise) {
+        vs_rng_load(g, a.rng_snap + (size_t)chunk_id * 32);
+        re = vs_load_entry(me.tab + rq);
+    }
+
+    if (!PAIRED) {
+        /* ======== flow mode: one warp, G then W ======== */
+        __syncwarp();
+        for (int w = 0; w < nwin; w++) {
+            if (DRAWS) { vs_draw_window(me, w, g, re, rq, draws + lane * VS_WIN); __syncwarp(); }
+            for (int j = 0; j < 32; j++)
+                vs_gen_row<MODE, NOISE>(tile0 + j * VS_TS, lanes[j], w, lane, pidx + j, draws + j * VS_WIN);
+            __syncwarp();
+            for (int j = 0; j < 32; j++) vs_write_row(tile0 + j * VS_TS, lanes[j], w, lane);
+            __syncwarp();
+        }
+        return;
+    }
+
+    /* ======== filtering modes: consumer F(w) overlaps producers' W(w-1) and G(w+1) ======== */
+    vs_named_barrier(1 + pair, group_threads);               /* row descriptors visible */
+    if (consumer) {
+        double y[VS_RING];
+        double cf[VS_ORDER + 1];
+#pragma unroll
+        for (int j = 0; j < VS_RING; j++) y[j] = 0.0;
+#pragma unroll
+        for (int j = 0; j <= VS_ORDER; j++) cf[j] = __ldg(a.coef + preset * VS_RING + j);
+        vs_named_barrier(1 + pair, group_threads);           /* window 0 generated */
+        for (int w = 0; w < nwin; w++) {
+            const int wb = me.blk0 + w * VS_WIN;
+            if (wb < me.hi)
+                vs_filter_window<EXACT, RAW, CHECKED>(
+                    reinterpret_cast<uint32_t *>(tile0 + (w & 1) * VS_TILE_I16 + lane * VS_TS), y, cf, gaind, pred, rrow,
+                    wb, me.lo, me.hi);
+            vs_named_barrier(1 + pair, group_threads);
+        }
+    } else {
+        /* producers: rows prod, prod+PW, ... of the group */
+        if (DRAWS) {
+            if (owner) vs_draw_window(me, 0, g, re, rq, draws + lane * VS_WIN);
+            vs_named_barrier(1 + VS_NP + pair, VS_PW * 32);
+        }
+        for (int j = prod; j < 32; j += VS_PW)
+            vs_gen_row<MODE, NOISE>(tile0 + j * VS_TS, lanes[j], 0, lane, pidx + j, draws + j * VS_WIN);
+        vs_named_barrier(1 + pair, group_threads);           /* window 0 generated */
+        for (int w = 0; w < nwin; w++) {
+            int16_t *other = tile0 + ((w + 1) & 1) * VS_TILE_I16;
+            if (w > 0)
+                for (int j = prod; j < 32; j += VS_PW) vs_write_row(other + j * VS_TS, lanes[j], w - 1, lane);
+            if (w + 1 < nwin) {
+                if (DRAWS) {
+                    if (owner) vs_draw_window(me, w + 1, g, re, rq, draws + lane * VS_WIN);
+                    vs_named_barrier(1 + VS_NP + pair, VS_PW * 32);
+                }
+                __syncwarp();
+                for (int j = prod; j < 32; j += VS_PW)
+                    vs_gen_row<MODE, NOISE>(other + j * VS_TS, lanes[j], w + 1, lane, pidx + j, draws + j * VS_WIN);
+            }
+            vs_named_barrier(1 + pair, group_threads);
+        }
+        if (nwin > 0) {
+            const int16_t *last = tile0 + ((nwin - 1) & 1) * VS_TILE_I16;
+            for (int j = prod; j < 32; j += VS_PW) vs_write_row(last + j * VS_TS, lanes[j], nwin - 1, lane);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * FP64 pipe peak: 8 independent DFMA chains per thread, every SM full.  Used by bench.py to put a
+ * measured denominator next to the HBM-write roofline.
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(256) vs_fp64_peak_kernel(double *out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+        x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b); x2 = __fma_rn(x2, a, b); x3 = __fma_rn(x3, a, b);
+        x4 = __fma_rn(x4, a, b); x5 = __fma_rn(x5, a, b); x6 = __fma_rn(x6, a, b); x7 = __fma_rn(x7, a, b);
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+cudaError_t vs_launch_fp64_peak(double *scratch, int blocks, int iters, cudaStream_t s)
+{
+    vs_fp64_peak_kernel<<<blocks, 256, 0, s>>>(scratch, iters, 0.999999, 1e-9);
+    return cudaGetLastError();
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -449,16 +705,30 @@ cudaError_t vs_launch_plan(const VsPlanArgs &a, bool want_log, cudaStream_t s)
     return cudaGetLastError();
 }
 
-cudaError_t vs_launch_render(const VsRenderArgs &a, int mode, bool noise, bool exact, cudaStream_t s)
+template <int MODE, bool NOISE, int FLAGS>
+static void vs_go(const VsRenderArgs &a, cudaStream_t s)
 {
     const unsigned grid = (a.n_chunks + VS_NT - 1) / VS_NT;
-#define VS_GO(M, N, E) vs_render_kernel<M, N, E><<<grid, VS_NT, 0, s>>>(a)
-    if (mode == VS_MODE_FLOW) { if (noise) VS_GO(VS_MODE_FLOW, true, false); else VS_GO(VS_MODE_FLOW, false, false); }
-    else if (mode == VS_MODE_FILTER) { if (exact) VS_GO(VS_MODE_FILTER, false, true); else VS_GO(VS_MODE_FILTER, false, false); }
-    else {
-        if (noise) { if (exact) VS_GO(VS_MODE_SYNTH, true, true); else VS_GO(VS_MODE_SYNTH, true, false); }
-        else       { if (exact) VS_GO(VS_MODE_SYNTH, false, true); else VS_GO(VS_MODE_SYNTH, false, false); }
-    }
-#undef VS_GO
+    const int dyn = VS_SMEM_BASE + ((NOISE && MODE != VS_MODE_FILTER) ? VS_SMEM_NOISE : 0);
+    cudaFuncSetAttribute(vs_render_kernel<MODE, NOISE, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    vs_render_kernel<MODE, NOISE, FLAGS><<<grid, MODE == VS_MODE_FLOW ? VS_NT : VS_THREADS_PAIRED, dyn, s>>>(a);
+}
+
+template <int MODE, bool NOISE>
+static void vs_go_flags(const VsRenderArgs &a, bool exact, cudaStream_t s)
+{
+    const bool raw = a.raw_out != nullptr;
+    if (exact) { if (raw) vs_go<MODE, NOISE, 3>(a, s); else vs_go<MODE, NOISE, 1>(a, s); }
+    else if (raw) vs_go<MODE, NOISE, 6>(a, s);                       /* raw output is a debug path: keep it checked */
+    else if (a.checked_quant) vs_go<MODE, NOISE, 4>(a, s);
+    else vs_go<MODE, NOISE, 0>(a, s);
+}
+
+cudaError_t vs_launch_render(const VsRenderArgs &a, int mode, bool noise, bool exact, cudaStream_t s)
+{
+    if (mode == VS_MODE_FLOW) { if (noise) vs_go<VS_MODE_FLOW, true, 0>(a, s); else vs_go<VS_MODE_FLOW, false, 0>(a, s); }
+    else if (mode == VS_MODE_FILTER) vs_go_flags<VS_MODE_FILTER, false>(a, exact, s);
+    else if (noise) vs_go_flags<VS_MODE_SYNTH, true>(a, exact, s);
+    else vs_go_flags<VS_MODE_SYNTH, false>(a, exact, s);
     return cudaGetLastError();
 }
