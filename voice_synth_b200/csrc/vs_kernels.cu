@@ -368,22 +368,34 @@ __device__ __forceinline__ int vs_quant_fast_nocheck(double v)
  * PRODUCER warps (G and W phases) over two tiles; in flow mode by a single warp doing G then W.   */
 #define VS_NP        4
 #define VS_PW        3
+#define VS_MAXSEG    4                     /* period segments a row can queue per bookkeeping pass */
 #define VS_TILE_I16  (32 * VS_TS)
 #define VS_THREADS_PAIRED ((VS_NP + VS_NP * VS_PW) * 32)
 
-#define VS_SMEM_TILES (VS_NP * 2 * VS_TILE_I16 * 2)
+/* one pitch period's share of one row's window: what the cooperative evaluation needs */
+struct __align__(16) VsSeg {
+    double Ad, Kd;
+    int rel;          /* tile index of the period's sample 0 (may be negative) */
+    int a0, a1;       /* in-period indices [a0,a1) that fall into this window  */
+    uint32_t T34;     /* T3 | T4<<16 (noise) */
+};
+
+/* NTILE = tiles per group: 2 (double buffer) in the filtering modes, 1 in flow mode */
+#define VS_SMEM_TILES(NTILE) (VS_NP * (NTILE) * VS_TILE_I16 * 2)
 #define VS_SMEM_LANES (VS_NP * 32 * (int)sizeof(VsLane))
-#define VS_SMEM_PIDX  (VS_NP * 32 * 4)
-#define VS_SMEM_BASE  (VS_SMEM_TILES + VS_SMEM_LANES + VS_SMEM_PIDX)
-#define VS_SMEM_NOISE ((VS_RNG_DEG * VS_NT + VS_NP * 32 * VS_WIN) * 4)
+#define VS_SMEM_SEGS  (VS_NP * 32 * VS_MAXSEG * (int)sizeof(VsSeg))
+#define VS_SMEM_NSEG  (VS_NP * 32 * 4)
+#define VS_SMEM_BASE(NTILE) (VS_SMEM_TILES(NTILE) + VS_SMEM_LANES + VS_SMEM_SEGS + VS_SMEM_NSEG)
+/* noise: RNG states [31][VS_NT] words + the window's noise samples [NP][32][VS_WIN] int16 */
+#define VS_SMEM_NOISE (VS_RNG_DEG * VS_NT * 4 + VS_NP * 32 * VS_WIN * 2)
 
 __device__ __forceinline__ void vs_named_barrier(int id, int count)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-/* ---- noise: lane = row; draw the row's random() values for window w into dr[sample - window base] -- */
-__device__ __forceinline__ void vs_draw_window(const VsLane &me, int w, VsRng &g, VsEnt &re, uint32_t &rq, int32_t *dr)
+/* ---- noise: lane = row; the row's noise samples w (flowgen_shimmer.c:387,398) for window w -------- */
+__device__ __forceinline__ void vs_draw_window(const VsLane &me, int w, VsRng &g, VsEnt &re, uint32_t &rq, int16_t *dr)
 {
     const int wb = me.blk0 + w * VS_WIN;
     if (!me.noise || wb >= me.hi) return;
@@ -395,77 +407,120 @@ __device__ __forceinline__ void vs_draw_window(const VsLane &me, int w, VsRng &g
             for (int k = 0; k < re.npert; k++) (void)vs_rng_next(g);
             i = m - re.start;
         }
-        if (i < re.T4 || i >= re.T3) dr[m - wb] = vs_rng_next(g);            /* :385, :396 */
+        if (i < re.T4 || i >= re.T3) dr[m - wb] = (int16_t)vs_noise_w(vs_rng_next(g), re.ndw);
     }
 }
 
-/* ---- G: the warp generates the VS_WIN samples of ONE row for window w ---------------------------------
- * Given the period table a sample depends only on its index: closed phase = DC (a word fill), rising
- * and falling branches are contiguous index segments of each period, evaluated 32 samples at a time. */
+/* ---- G: generate window w of the rows {row0, row0+step, ...} of a tile --------------------------------
+ * Given the period table a sample depends only on its index.  Closed phase = DC: a word fill.  The
+ * open phase of a period (rising then falling branch, flowgen_shimmer.c:318-332) is one contiguous
+ * index run.  Bookkeeping is lane-parallel (lane l <-> row row0 + l*step): each lane walks its row's
+ * period table and queues segment descriptors in shared memory; then the warp evaluates every queued
+ * run cooperatively, 32 consecutive samples per step, rising and falling through one code path. */
 template <int MODE, bool NOISE>
-__device__ __forceinline__ void vs_gen_row(int16_t *trow, const VsLane &L, int w, int lane, uint32_t *pidx_slot,
-                                           const int32_t *drow)
+__device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, VsSeg *segs, int *nsegs, int w, int lane,
+                                            int row0, int step, const VsLane &mine, uint32_t &q, const int16_t *noisebuf)
 {
-    const int wb = L.blk0 + w * VS_WIN;
-    if (wb >= L.hi) return;
-    const int glo = max(wb, L.nstart), ghi = min(wb + VS_WIN, L.hi);     /* samples that exist */
+    const int myrow = row0 + lane * step;
+    const bool have_row = myrow < 32;
 
     if (MODE == VS_MODE_FILTER) {
+        for (int j = row0; j < 32; j += step) {
+            const VsLane L = lanes[j];
+            const int wb = L.blk0 + w * VS_WIN;
+            if (wb >= L.hi) continue;
+            int16_t *trow = tile + j * VS_TS;
 #pragma unroll
-        for (int k = lane; k < VS_WIN; k += 32) {
-            const int m = wb + k;
-            trow[k] = (m >= glo && m < ghi) ? __ldg(L.fin + m) : (int16_t)0;
+            for (int k = lane; k < VS_WIN; k += 32) {
+                const int m = wb + k;
+                trow[k] = (m >= L.nstart && m < L.hi) ? __ldg(L.fin + m) : (int16_t)0;
+            }
         }
         return;
     }
 
-    /* closed phase everywhere (flowgen_shimmer.c:334-336), zeros outside the stream */
-    if (glo == wb && ghi == wb + VS_WIN) {
-        const uint32_t pat = (uint32_t)(uint16_t)L.DCs * 0x10001u;
-        uint32_t *t32 = reinterpret_cast<uint32_t *>(trow);
+    /* 1. closed phase everywhere (:334-336), zeros outside the stream */
+    for (int j = row0; j < 32; j += step) {
+        const int wb = lanes[j].blk0 + w * VS_WIN, hi = lanes[j].hi, ns = lanes[j].nstart;
+        if (wb >= hi) continue;
+        int16_t *trow = tile + j * VS_TS;
+        const int dcs = lanes[j].DCs;
+        if (ns <= wb && wb + VS_WIN <= hi) {
+            const uint32_t pat = (uint32_t)(uint16_t)dcs * 0x10001u;
+            uint32_t *t32 = reinterpret_cast<uint32_t *>(trow);
 #pragma unroll
-        for (int k = lane; k < VS_WIN / 2; k += 32) t32[k] = pat;
-    } else {
+            for (int k = lane; k < VS_WIN / 2; k += 32) t32[k] = pat;
+        } else {
 #pragma unroll
-        for (int k = lane; k < VS_WIN; k += 32) {
-            const int m = wb + k;
-            trow[k] = (m >= glo && m < ghi) ? (int16_t)L.DCs : (int16_t)0;
+            for (int k = lane; k < VS_WIN; k += 32) {
+                const int m = wb + k;
+                trow[k] = (m >= ns && m < hi) ? (int16_t)dcs : (int16_t)0;
+            }
         }
     }
-    __syncwarp();
 
-    const int T2 = L.T2, DCi = L.DCi;
-    const double *ct = L.ct, *ht = L.ct + T2;
-    uint32_t q = *pidx_slot;
-    int pend;
-    for (;;) {
-        const VsEnt e = vs_load_entry(L.tab + q);
-        pend = e.start + e.T;
-        if (pend > glo) {
-            const int rel = e.start - wb;                                 /* tile index of the period's sample 0 */
-            const int a0 = max(0, glo - e.start), a1 = min(e.T, ghi - e.start);       /* in-period index range */
-            /* rising branch (:318-324): i in [0,T2) */
-            for (int i = a0 + lane; i < min(a1, T2); i += 32) {
-                const int v = vs_rising(e.Ad, __ldg(ht + i));
-                if (v >= DCi) trow[rel + i] = (int16_t)v;
-            }
-            /* falling branch (:327-332): i in [T2,2*T2); once below DC it stays below (monotone) */
-            for (int i = max(a0, T2) + lane; i < min(a1, 2 * T2); i += 32) {
-                const int v = vs_falling(e.Ad, e.Kd, __ldg(ct + i - T2));
-                if (v >= DCi) trow[rel + i] = (int16_t)v;
-            }
-            if (NOISE && L.noise) {                                       /* :385-406 */
-                __syncwarp();
-                for (int i = a0 + lane; i < min(a1, e.T4); i += 32)
-                    trow[rel + i] = (int16_t)vs_add_clip(trow[rel + i], vs_noise_w(drow[rel + i], e.ndw));
-                for (int i = max(a0, e.T3) + lane; i < a1; i += 32)
-                    trow[rel + i] = (int16_t)vs_add_clip(trow[rel + i], vs_noise_w(drow[rel + i], e.ndw));
+    /* 2. bookkeeping passes + cooperative evaluation */
+    const int wb_m = mine.blk0 + w * VS_WIN;
+    const int glo = max(wb_m, mine.nstart), ghi = min(wb_m + VS_WIN, mine.hi);
+    bool pending = have_row && wb_m < mine.hi;
+    while (__any_sync(VS_FULL, pending)) {
+        int n = 0;
+        if (pending) {
+            VsSeg *my = segs + myrow * VS_MAXSEG;
+            const int open_end = 2 * mine.T2;
+#pragma unroll 1
+            for (int sidx = 0; sidx < VS_MAXSEG; sidx++) {
+                const VsEnt e = vs_load_entry(mine.tab + q);
+                const int pend = e.start + e.T;
+                if (pend > glo) {
+                    const int a0 = max(0, glo - e.start), a1 = min(e.T, ghi - e.start);
+                    if (a0 < min(a1, open_end) || (NOISE && mine.noise)) {
+                        VsSeg sg;
+                        sg.Ad = e.Ad; sg.Kd = e.Kd; sg.rel = e.start - wb_m; sg.a0 = a0; sg.a1 = a1;
+                        sg.T34 = (uint32_t)e.T3 | ((uint32_t)e.T4 << 16);
+                        my[n++] = sg;
+                    }
+                }
+                if (pend >= ghi) {                       /* window covered: q -> period of the next window's first sample */
+                    if (pend == ghi) q++;
+                    pending = false;
+                    break;
+                }
+                q++;
             }
         }
-        if (pend >= ghi) break;
-        q++;
+        if (have_row) nsegs[myrow] = n;
+        __syncwarp();
+
+        for (int j = row0; j < 32; j += step) {
+            const int cnt = nsegs[j];
+            if (cnt == 0) continue;
+            const VsLane L = lanes[j];
+            int16_t *trow = tile + j * VS_TS;
+            const int T2 = L.T2, DCi = L.DCi;
+            const double *ct = L.ct;
+            for (int sidx = 0; sidx < cnt; sidx++) {
+                const VsSeg sg = segs[j * VS_MAXSEG + sidx];
+                const int o1 = min(sg.a1, 2 * T2);
+                for (int i = sg.a0 + lane; i < o1; i += 32) {
+                    const bool rising = i < T2;
+                    const double tv = __ldg(ct + (rising ? i + T2 : i - T2));      /* h[i] or c[i-T2] */
+                    const double fall = __dadd_rn(__dsub_rn(__dmul_rn(sg.Kd, tv), sg.Kd), 1.0);
+                    const int v = vs_ceil_s16(__dmul_rn(sg.Ad, rising ? tv : fall));
+                    if (v >= DCi) trow[sg.rel + i] = (int16_t)v;
+                }
+                if (NOISE && L.noise) {                                             /* :385-406 */
+                    __syncwarp();
+                    const int T3 = (int)(sg.T34 & 0xffffu), T4 = (int)(sg.T34 >> 16);
+                    const int16_t *nrow = noisebuf + j * VS_WIN;
+                    for (int i = sg.a0 + lane; i < sg.a1; i += 32)
+                        if (i < T4 || i >= T3)
+                            trow[sg.rel + i] = (int16_t)vs_add_clip(trow[sg.rel + i], nrow[sg.rel + i]);
+                }
+            }
+        }
+        __syncwarp();
     }
-    if (lane == 0) *pidx_slot = pend > ghi ? q : q + 1;                   /* period holding the next window's first sample */
 }
 
 /* ---- W: one row, whole 16-byte pieces, consecutive lanes on consecutive pieces ----------------------- */
@@ -542,27 +597,33 @@ vs_render_kernel(const VsRenderArgs a)
     constexpr bool DRAWS = NOISE && MODE != VS_MODE_FILTER;
     constexpr bool EXACT = (FLAGS & 1) != 0, RAW = (FLAGS & 2) != 0, CHECKED = (FLAGS & 4) != 0;
     extern __shared__ __align__(16) unsigned char s_raw[];
+    constexpr int NTILE = PAIRED ? 2 : 1;
     int16_t *s_tiles = reinterpret_cast<int16_t *>(s_raw);
-    VsLane *s_lanes = reinterpret_cast<VsLane *>(s_raw + VS_SMEM_TILES);
-    uint32_t *s_pidx = reinterpret_cast<uint32_t *>(s_raw + VS_SMEM_TILES + VS_SMEM_LANES);
-    uint32_t *s_rng = reinterpret_cast<uint32_t *>(s_raw + VS_SMEM_BASE);
-    int32_t *s_draws = reinterpret_cast<int32_t *>(s_raw + VS_SMEM_BASE) + VS_RNG_DEG * VS_NT;
+    VsLane *s_lanes = reinterpret_cast<VsLane *>(s_raw + VS_SMEM_TILES(NTILE));
+    VsSeg *s_segs = reinterpret_cast<VsSeg *>(s_raw + VS_SMEM_TILES(NTILE) + VS_SMEM_LANES);
+    int *s_nseg = reinterpret_cast<int *>(s_raw + VS_SMEM_TILES(NTILE) + VS_SMEM_LANES + VS_SMEM_SEGS);
+    uint32_t *s_rng = reinterpret_cast<uint32_t *>(s_raw + VS_SMEM_BASE(NTILE));
+    int16_t *s_noise = reinterpret_cast<int16_t *>(s_raw + VS_SMEM_BASE(NTILE) + VS_RNG_DEG * VS_NT * 4);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int pair = warp % VS_NP;                       /* warps 0..NP-1 consume, NP.. produce */
     const int prod = PAIRED ? warp / VS_NP - 1 : 0;      /* producer index inside the group, -1 = consumer */
     const bool consumer = PAIRED && warp < VS_NP;
-    const bool owner = PAIRED ? prod == 0 : true;        /* the warp that sets a group up and owns its RNGs */
-    const uint32_t t = blockIdx.x * VS_NT + pair * 32 + lane;   /* row slot of this lane */
-    const bool active = t < a.n_chunks;
-    int16_t *tile0 = s_tiles + pair * 2 * VS_TILE_I16;
+    const int step = PAIRED ? VS_PW : 1;                 /* a producer warp works rows prod, prod+step, ... */
+    int16_t *tile0 = s_tiles + pair * NTILE * VS_TILE_I16;
     VsLane *lanes = s_lanes + pair * 32;
-    uint32_t *pidx = s_pidx + pair * 32;
-    int32_t *draws = s_draws + pair * 32 * VS_WIN;
+    VsSeg *segs = s_segs + pair * 32 * VS_MAXSEG;
+    int *nsegs = s_nseg + pair * 32;
+    int16_t *noisebuf = s_noise + pair * 32 * VS_WIN;
     const int group_threads = (1 + VS_PW) * 32;
 
-    /* ---- per-row setup (every warp of the group computes its own copy; the owner publishes it) ----- */
-    uint32_t first_pidx = 0, chunk_id = 0;
+    /* Row of this lane.  Consumer lane l filters row l; producer lane l keeps the books of row
+     * prod + l*step (and, with noise, owns that row's RNG). */
+    const int myrow = consumer ? lane : prod + lane * step;
+    const uint32_t t = blockIdx.x * VS_NT + pair * 32 + (uint32_t)myrow;
+    const bool active = myrow < 32 && t < a.n_chunks;
+
+    uint32_t q = 0, chunk_id = 0;
     int preset = 0;
     double gaind = 0.0, pred = 0.0;
     double *rrow = nullptr;
@@ -585,38 +646,39 @@ vs_render_kernel(const VsRenderArgs a)
             me.DCi = (int)ceilf(st.DC);
             me.DCs = st.DCs;
             me.noise = (st.flags & VS_F_NOISE) ? 1 : 0;
-            first_pidx = ck.first_period;
-            me.nstart = (int)__ldg(&me.tab[first_pidx].start);
+            q = ck.first_period;
+            me.nstart = (int)__ldg(&me.tab[q].start);
         }
         const int phase = (int)((reinterpret_cast<uintptr_t>(me.orow) >> 1) & 7);
         me.blk0 = me.nstart - ((phase + me.nstart) & 7);
         preset = st.preset; gaind = (double)st.gain; pred = (double)st.pre;
         rrow = (RAW && a.raw_out) ? a.raw_out + st.out_off : nullptr;
     }
+    /* windows to run: max over the 32 rows of the group (each warp of the group sees a subset) */
     int nwin = active ? (me.hi - me.blk0 + VS_WIN - 1) / VS_WIN : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nwin = max(nwin, __shfl_xor_sync(VS_FULL, nwin, o));
-    if (owner) { lanes[lane] = me; pidx[lane] = first_pidx; }
+    if (!consumer && myrow < 32) lanes[myrow] = me;          /* producers publish the row descriptors */
 
-    /* noise: the owner warp's lane j owns row j's RNG, restored from the plan kernel's snapshot */
+    /* noise: the book-keeping lane owns its row's RNG, restored from the plan kernel's snapshot */
     VsRng g;
-    g.r = s_rng + (DRAWS ? pair * 32 + lane : 0);
+    g.r = s_rng + (DRAWS ? pair * 32 + (myrow & 31) : 0);
     g.f = 3;
     VsEnt re;
     re.start = 0; re.T = 0x7fffffff; re.T3 = 0; re.T4 = 0; re.npert = 0; re.ndw = 0; re.Ad = re.Kd = 0.0;
-    uint32_t rq = first_pidx;
-    if (DRAWS && owner && active && me.noise) {
+    uint32_t rq = q;
+    if (DRAWS && !consumer && active && me.noise) {
         vs_rng_load(g, a.rng_snap + (size_t)chunk_id * 32);
         re = vs_load_entry(me.tab + rq);
     }
+    int16_t *mynoise = noisebuf + (myrow & 31) * VS_WIN;
 
     if (!PAIRED) {
         /* ======== flow mode: one warp, G then W ======== */
         __syncwarp();
         for (int w = 0; w < nwin; w++) {
-            if (DRAWS) { vs_draw_window(me, w, g, re, rq, draws + lane * VS_WIN); __syncwarp(); }
-            for (int j = 0; j < 32; j++)
-                vs_gen_row<MODE, NOISE>(tile0 + j * VS_TS, lanes[j], w, lane, pidx + j, draws + j * VS_WIN);
+            if (DRAWS) { if (active) vs_draw_window(me, w, g, re, rq, mynoise); __syncwarp(); }
+            vs_gen_tile<MODE, NOISE>(tile0, lanes, segs, nsegs, w, lane, 0, 1, me, q, noisebuf);
             __syncwarp();
             for (int j = 0; j < 32; j++) vs_write_row(tile0 + j * VS_TS, lanes[j], w, lane);
             __syncwarp();
@@ -625,7 +687,13 @@ vs_render_kernel(const VsRenderArgs a)
     }
 
     /* ======== filtering modes: consumer F(w) overlaps producers' W(w-1) and G(w+1) ======== */
-    vs_named_barrier(1 + pair, group_threads);               /* row descriptors visible */
+    {
+        /* the group's window count: consumers saw all 32 rows, producers only theirs -> share the max */
+        __shared__ int s_groupwin[VS_NP];
+        if (consumer && lane == 0) s_groupwin[pair] = nwin;
+        vs_named_barrier(1 + pair, group_threads);           /* row descriptors + window count visible */
+        nwin = s_groupwin[pair];
+    }
     if (consumer) {
         double y[VS_RING];
         double cf[VS_ORDER + 1];
@@ -636,39 +704,31 @@ vs_render_kernel(const VsRenderArgs a)
         vs_named_barrier(1 + pair, group_threads);           /* window 0 generated */
         for (int w = 0; w < nwin; w++) {
             const int wb = me.blk0 + w * VS_WIN;
-            if (wb < me.hi)
+            if (active && wb < me.hi)
                 vs_filter_window<EXACT, RAW, CHECKED>(
                     reinterpret_cast<uint32_t *>(tile0 + (w & 1) * VS_TILE_I16 + lane * VS_TS), y, cf, gaind, pred, rrow,
                     wb, me.lo, me.hi);
             vs_named_barrier(1 + pair, group_threads);
         }
     } else {
-        /* producers: rows prod, prod+PW, ... of the group */
-        if (DRAWS) {
-            if (owner) vs_draw_window(me, 0, g, re, rq, draws + lane * VS_WIN);
-            vs_named_barrier(1 + VS_NP + pair, VS_PW * 32);
-        }
-        for (int j = prod; j < 32; j += VS_PW)
-            vs_gen_row<MODE, NOISE>(tile0 + j * VS_TS, lanes[j], 0, lane, pidx + j, draws + j * VS_WIN);
+        if (DRAWS && active) vs_draw_window(me, 0, g, re, rq, mynoise);
+        __syncwarp();
+        vs_gen_tile<MODE, NOISE>(tile0, lanes, segs, nsegs, 0, lane, prod, step, me, q, noisebuf);
         vs_named_barrier(1 + pair, group_threads);           /* window 0 generated */
         for (int w = 0; w < nwin; w++) {
             int16_t *other = tile0 + ((w + 1) & 1) * VS_TILE_I16;
             if (w > 0)
-                for (int j = prod; j < 32; j += VS_PW) vs_write_row(other + j * VS_TS, lanes[j], w - 1, lane);
+                for (int j = prod; j < 32; j += step) vs_write_row(other + j * VS_TS, lanes[j], w - 1, lane);
             if (w + 1 < nwin) {
-                if (DRAWS) {
-                    if (owner) vs_draw_window(me, w + 1, g, re, rq, draws + lane * VS_WIN);
-                    vs_named_barrier(1 + VS_NP + pair, VS_PW * 32);
-                }
+                if (DRAWS && active) vs_draw_window(me, w + 1, g, re, rq, mynoise);
                 __syncwarp();
-                for (int j = prod; j < 32; j += VS_PW)
-                    vs_gen_row<MODE, NOISE>(other + j * VS_TS, lanes[j], w + 1, lane, pidx + j, draws + j * VS_WIN);
+                vs_gen_tile<MODE, NOISE>(other, lanes, segs, nsegs, w + 1, lane, prod, step, me, q, noisebuf);
             }
             vs_named_barrier(1 + pair, group_threads);
         }
         if (nwin > 0) {
             const int16_t *last = tile0 + ((nwin - 1) & 1) * VS_TILE_I16;
-            for (int j = prod; j < 32; j += VS_PW) vs_write_row(last + j * VS_TS, lanes[j], nwin - 1, lane);
+            for (int j = prod; j < 32; j += step) vs_write_row(last + j * VS_TS, lanes[j], nwin - 1, lane);
         }
     }
 }
@@ -709,7 +769,7 @@ template <int MODE, bool NOISE, int FLAGS>
 static void vs_go(const VsRenderArgs &a, cudaStream_t s)
 {
     const unsigned grid = (a.n_chunks + VS_NT - 1) / VS_NT;
-    const int dyn = VS_SMEM_BASE + ((NOISE && MODE != VS_MODE_FILTER) ? VS_SMEM_NOISE : 0);
+    const int dyn = VS_SMEM_BASE(MODE == VS_MODE_FLOW ? 1 : 2) + ((NOISE && MODE != VS_MODE_FILTER) ? VS_SMEM_NOISE : 0);
     cudaFuncSetAttribute(vs_render_kernel<MODE, NOISE, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     vs_render_kernel<MODE, NOISE, FLAGS><<<grid, MODE == VS_MODE_FLOW ? VS_NT : VS_THREADS_PAIRED, dyn, s>>>(a);
 }
