@@ -26,3 +26,22 @@ for name, opts in [("auto", {}), ("nochunk", {1: -1}), ("L2048", {1: 2048}), ("L
               "Msamples/s(render)", round(best["samples"] / best["render_ms"] / 1e3, 1), flush=True)
     for k in opts:
         ctx.set_option(k, 0 if k == 1 else 2.0)
+
+# filter-only on device-resident flow: the F-bound rate (producers only copy)
+flow = torch.zeros(int(ns.sum()), dtype=torch.int16, device="cuda")
+ctx.flowgen_batch(p, out=flow)
+offs = (torch.arange(p.n, dtype=torch.int64) * int(ns.max())).numpy().astype(np.uint64)
+for name, opts in [("auto", {}), ("L5512", {1: 5512}), ("L2756", {1: 2756})]:
+    for k, v in opts.items():
+        ctx.set_option(k, v)
+    best = None
+    for it in range(4):
+        ctx.vowel_filter_batch(flow, ns, f, out=dev)
+        t = ctx.timing()
+        if best is None or t["render_ms"] < best["render_ms"]:
+            best = t
+    print(name, "filter", {k: (round(v, 4) if isinstance(v, float) else v) for k, v in best.items()},
+          "Msamples/s(render)", round(best["samples"] / best["render_ms"] / 1e3, 1), flush=True)
+    for k in opts:
+        ctx.set_option(k, 0)
+print("fp64 peak (TFLOP/s, implied MHz):", ctx.fp64_peak())

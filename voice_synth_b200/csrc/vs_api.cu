@@ -51,6 +51,8 @@ struct Slot {
     cudaEvent_t h2d_done = nullptr;
     cudaEvent_t slab_done[2] = {nullptr, nullptr};   /* D2H of the slab using pcm[k] finished */
     cudaEvent_t slab_ready = nullptr;                /* render of the current slab finished   */
+    cudaStream_t pstream[VS_NUM_PRESETS] = {};       /* one side stream per vowel preset: the per-preset   */
+    cudaEvent_t pfork = nullptr, pjoin[VS_NUM_PRESETS] = {};   /* render launches of a slab run concurrently */
     DevBuf streams, chunks, order, table, snap, nper, costab, coef, status, pcm[2], raw[2], flowin[2], log;
     PinBuf h_streams, h_chunks, h_order, h_nper, h_status;
     size_t costab_uploaded = 0;
@@ -268,18 +270,21 @@ uint32_t cos_table_for(vs_ctx *ctx, int T2)
     const uint32_t off = (uint32_t)ctx->cos_host.size();
     volatile double one = 1.0;
     const double pi = 4.0 * std::atan(one);                           /* #define PI 4.0*atan(1.0) (:39) */
+    /* layout per T2: h[0..T2) then c[0..T2), so that the open-phase index i in [0,2*T2) addresses it
+     * directly.  h[i] = 0.5*(1-c[i]): (A*0.5)*(1.0-c) == A*h bit for bit, scaling by 0.5 being exact (:319) */
+    std::vector<double> c((size_t)T2);
     for (int i = 0; i < T2; i++) {
         volatile double num = pi * i;                                 /* PI*i/T2 == ((4.0*atan(1.0))*i)/T2 */
         volatile double arg = num / T2;
-        ctx->cos_host.push_back(std::cos(arg));
+        c[i] = std::cos(arg);
     }
-    /* h[i] = 0.5*(1-c[i]): (A*0.5)*(1.0-c) == A*h bit for bit, scaling by 0.5 being exact (:319) */
     for (int i = 0; i < T2; i++) {
-        volatile double om = 1.0 - ctx->cos_host[off + i];
+        volatile double om = 1.0 - c[i];
         volatile double h = 0.5 * om;
         const double hv = h;
         ctx->cos_host.push_back(hv);
     }
+    for (int i = 0; i < T2; i++) ctx->cos_host.push_back(c[i]);
     ctx->cos_index[T2] = off;
     return off;
 }
@@ -503,14 +508,38 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         }
         slab_c0[n_slabs] = hc.size();
         const size_t nc = hc.size();
-        /* render order: longest chunks first inside each slab, so that the 32 lanes of a warp run
-         * windows of similar count and the tail of the grid is made of short chunks */
-        std::vector<uint32_t> order(nc);
-        for (size_t c = 0; c < nc; c++) order[c] = (uint32_t)c;
-        for (size_t k = 0; k < n_slabs; k++)
-            std::stable_sort(order.begin() + slab_c0[k], order.begin() + slab_c0[k + 1], [&](uint32_t x, uint32_t y) {
+        /* render rows: inside each slab the chunks are grouped by vowel preset (a CTA serves one
+         * preset, so its coefficients sit in uniform registers), longest first inside a preset (the
+         * 32 lanes of a warp then run a similar number of windows), and every preset group is padded
+         * to a whole CTA with VS_NO_CHUNK rows */
+        std::vector<uint32_t> order;
+        struct Group { size_t r0, r1; int preset; };             /* rows [r0,r1) of one preset = one launch */
+        std::vector<std::vector<Group>> slab_groups(n_slabs);
+        std::vector<size_t> slab_r0(n_slabs + 1, 0);
+        for (size_t k = 0; k < n_slabs; k++) {
+            slab_r0[k] = order.size();
+            std::vector<uint32_t> ids(slab_c0[k + 1] - slab_c0[k]);
+            for (size_t c = 0; c < ids.size(); c++) ids[c] = (uint32_t)(slab_c0[k] + c);
+            auto preset_of = [&](uint32_t c) -> int { return b.mode == VS_MODE_FLOW ? 0 : hs[s0 + hc[c].stream].preset; };
+            std::stable_sort(ids.begin(), ids.end(), [&](uint32_t x, uint32_t y) {
+                const int px = preset_of(x), py = preset_of(y);
+                if (px != py) return px < py;
                 return hc[x].emit_hi - hc[x].gen_target > hc[y].emit_hi - hc[y].gen_target;
             });
+            size_t i0 = 0;
+            while (i0 < ids.size()) {
+                size_t i1 = i0;
+                const int pr = preset_of(ids[i0]);
+                while (i1 < ids.size() && preset_of(ids[i1]) == pr) i1++;
+                const size_t r0 = order.size();
+                for (size_t i = i0; i < i1; i++) order.push_back(ids[i]);
+                while (order.size() % VS_NT) order.push_back(VS_NO_CHUNK);
+                slab_groups[k].push_back({r0, order.size(), pr});
+                i0 = i1;
+            }
+        }
+        slab_r0[n_slabs] = order.size();
+        const size_t nrows = order.size();
         ctx->timing.chunks += (uint32_t)nc;
         ctx->timing.samples += total;
         ctx->timing.warmup_samples += warm_total;
@@ -519,11 +548,11 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         int rc;
         if ((rc = dev_reserve(ctx, sl, sl.streams, ns * sizeof(VsStream)))) return rc;
         if ((rc = dev_reserve(ctx, sl, sl.chunks, nc * sizeof(VsChunk)))) return rc;
-        if ((rc = dev_reserve(ctx, sl, sl.order, nc * sizeof(uint32_t)))) return rc;
+        if ((rc = dev_reserve(ctx, sl, sl.order, nrows * sizeof(uint32_t) + 16))) return rc;
         if ((rc = dev_reserve(ctx, sl, sl.nper, ns * sizeof(uint32_t)))) return rc;
         if ((rc = dev_reserve(ctx, sl, sl.status, sizeof(int32_t)))) return rc;
         if (b.mode != VS_MODE_FILTER) {
-            if ((rc = dev_reserve(ctx, sl, sl.table, tab_total * sizeof(VsPeriod)))) return rc;
+            if ((rc = dev_reserve(ctx, sl, sl.table, (tab_total + 8) * sizeof(VsPeriod)))) return rc;
             if (any_noise && (rc = dev_reserve(ctx, sl, sl.snap, nc * 32 * sizeof(uint32_t)))) return rc;
             if ((rc = dev_reserve(ctx, sl, sl.costab, std::max<size_t>(8, ctx->cos_host.size() * sizeof(double))))) return rc;
             if (sl.costab_uploaded != ctx->cos_host.size()) {
@@ -535,7 +564,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         }
         if ((rc = pin_reserve(ctx, sl.h_streams, ns * sizeof(VsStream)))) return rc;
         if ((rc = pin_reserve(ctx, sl.h_chunks, nc * sizeof(VsChunk)))) return rc;
-        if ((rc = pin_reserve(ctx, sl.h_order, nc * sizeof(uint32_t)))) return rc;
+        if ((rc = pin_reserve(ctx, sl.h_order, nrows * sizeof(uint32_t) + 16))) return rc;
         if ((rc = pin_reserve(ctx, sl.h_nper, ns * sizeof(uint32_t)))) return rc;
         if ((rc = pin_reserve(ctx, sl.h_status, sizeof(int32_t)))) return rc;
 
@@ -595,11 +624,11 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             }
         }
         memcpy(sl.h_chunks.p, hc.data(), nc * sizeof(VsChunk));
-        memcpy(sl.h_order.p, order.data(), nc * sizeof(uint32_t));
+        memcpy(sl.h_order.p, order.data(), nrows * sizeof(uint32_t));
         *(int32_t *)sl.h_status.p = 0;
         CU(cudaMemcpyAsync(sl.streams.p, sl.h_streams.p, ns * sizeof(VsStream), cudaMemcpyHostToDevice, sl.compute));
         CU(cudaMemcpyAsync(sl.chunks.p, sl.h_chunks.p, nc * sizeof(VsChunk), cudaMemcpyHostToDevice, sl.compute));
-        CU(cudaMemcpyAsync(sl.order.p, sl.h_order.p, nc * sizeof(uint32_t), cudaMemcpyHostToDevice, sl.compute));
+        CU(cudaMemcpyAsync(sl.order.p, sl.h_order.p, nrows * sizeof(uint32_t), cudaMemcpyHostToDevice, sl.compute));
         CU(cudaMemsetAsync(sl.status.p, 0, sizeof(int32_t), sl.compute));
 
         cudaEvent_t t_first = nullptr;
@@ -649,7 +678,6 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             memset(&ra, 0, sizeof ra);
             ra.streams = (const VsStream *)sl.streams.p;
             ra.chunks = (const VsChunk *)sl.chunks.p;
-            ra.order = (const uint32_t *)sl.order.p + c0;
             ra.n_chunks = (uint32_t)(c1 - c0);
             ra.table = (const VsPeriod *)sl.table.p;
             ra.rng_snap = any_noise ? (const uint32_t *)sl.snap.p : nullptr;
@@ -659,8 +687,26 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             ra.pcm_out = d_pcm;
             ra.raw_out = d_raw;
             ra.checked_quant = checked_quant ? 1 : 0;
-            CU(vs_launch_render(ra, b.mode, any_noise, exact, sl.compute));
-            ctx->timing.launches++;
+            /* one launch per vowel preset (its coefficients travel as kernel parameters); with more
+             * than one preset the launches fork onto side streams so that they share the SMs */
+            const std::vector<Group> &groups = slab_groups[k];
+            const bool fork = groups.size() > 1;
+            if (fork) CU(cudaEventRecord(sl.pfork, sl.compute));
+            for (size_t gi = 0; gi < groups.size(); gi++) {
+                const Group &gr = groups[gi];
+                ra.order = (const uint32_t *)sl.order.p + gr.r0;
+                ra.n_rows = (uint32_t)(gr.r1 - gr.r0);
+                for (int j = 0; j < VS_RING; j++) ra.ncf[j] = j <= VS_ORDER ? -vs_preset_den[gr.preset][j] : 0.0;
+                cudaStream_t st = fork ? sl.pstream[gi % VS_NUM_PRESETS] : sl.compute;
+                if (fork && gi < VS_NUM_PRESETS) CU(cudaStreamWaitEvent(st, sl.pfork, 0));
+                CU(vs_launch_render(ra, b.mode, any_noise, exact, st));
+                ctx->timing.launches++;
+            }
+            if (fork)
+                for (size_t gi = 0; gi < std::min<size_t>(groups.size(), VS_NUM_PRESETS); gi++) {
+                    CU(cudaEventRecord(sl.pjoin[gi], sl.pstream[gi]));
+                    CU(cudaStreamWaitEvent(sl.compute, sl.pjoin[gi], 0));
+                }
             if (g == 0) CU(cudaEventRecord(e2, sl.compute));
 
             if (!out_dev) {
@@ -777,9 +823,13 @@ int vs_ctx_create(vs_ctx **out, const int *devices, int n_devices, uint32_t flag
                   cudaEventCreateWithFlags(&s.slab_done[0], cudaEventDisableTiming) == cudaSuccess &&
                   cudaEventCreateWithFlags(&s.slab_done[1], cudaEventDisableTiming) == cudaSuccess &&
                   cudaEventCreateWithFlags(&s.slab_ready, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&s.pfork, cudaEventDisableTiming) == cudaSuccess &&
                   cudaMalloc(&s.coef.p, coef.size() * sizeof(double)) == cudaSuccess &&
                   cudaMemcpy(s.coef.p, coef.data(), coef.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
         s.coef.cap = coef.size() * sizeof(double);
+        for (int k = 0; ok && k < VS_NUM_PRESETS; k++)
+            ok = cudaStreamCreateWithFlags(&s.pstream[k], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&s.pjoin[k], cudaEventDisableTiming) == cudaSuccess;
         ctx->slots.push_back(s);
         if (!ok) { cudaGetLastError(); vs_ctx_destroy(ctx); return VS_ECUDA; }
     }
@@ -804,6 +854,11 @@ void vs_ctx_destroy(vs_ctx *ctx)
         if (s.slab_done[0]) cudaEventDestroy(s.slab_done[0]);
         if (s.slab_done[1]) cudaEventDestroy(s.slab_done[1]);
         if (s.slab_ready) cudaEventDestroy(s.slab_ready);
+        if (s.pfork) cudaEventDestroy(s.pfork);
+        for (int k = 0; k < VS_NUM_PRESETS; k++) {
+            if (s.pjoin[k]) cudaEventDestroy(s.pjoin[k]);
+            if (s.pstream[k]) cudaStreamDestroy(s.pstream[k]);
+        }
         if (s.copy) cudaStreamDestroy(s.copy);
         if (s.compute && s.own_compute) cudaStreamDestroy(s.compute);
     }

@@ -8,6 +8,7 @@
 #define VS_RING    24          /* state ring / samples per unrolled filter block (>= VS_ORDER, 3 x 16 B of PCM) */
 #define VS_NT      128         /* threads per CTA of the plan and render kernels */
 #define VS_RNG_DEG 31          /* glibc TYPE_3 */
+#define VS_NO_CHUNK 0xffffffffu
 #define VS_WIN     192         /* samples per stream per render window (8 ring blocks, 24 x 16 B)  */
 #define VS_TS      194         /* tile row stride in int16: 97 words, odd => conflict-free columns  */
 
@@ -72,7 +73,10 @@ struct VsPlanArgs {
 struct VsRenderArgs {
     const VsStream *streams;
     const VsChunk  *chunks;
-    const uint32_t *order;          /* render thread t works on chunk order[t] (sorted by length)   */
+    const uint32_t *order;          /* render row t works on chunk order[t]; VS_NO_CHUNK = padding   */
+    double          ncf[VS_RING];   /* -A[j] of the ONE vowel preset this launch serves: as kernel
+                                       parameters they are constant-bank immediates of the DFMAs   */
+    uint32_t        n_rows;         /* rows incl. padding, multiple of VS_NT                         */
     uint32_t        n_chunks;
     const VsPeriod *table;
     const uint32_t *rng_snap;

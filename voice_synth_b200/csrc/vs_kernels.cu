@@ -31,6 +31,12 @@
 #include "vs_internal.h"
 
 #define VS_RAND_MAX_D 2147483647.0
+
+/* Filter coefficients reach the DFMAs as constant-bank operands (kernel parameters, VsRenderArgs::ncf;
+ * one launch per vowel preset).  On B200 a DFMA with two register operands + one constant operand
+ * issues every ~2.2 cycles per SM sub-partition, with three register operands only every ~3.1
+ * (measured: tests/tools/dfma_ops.cu), so per-lane coefficient registers would cap the filter at
+ * ~70 % of the FP64 pipe. */
 #define VS_FULL 0xffffffffu
 
 /* ------------------------------------------------------------------------------------------------
@@ -163,8 +169,8 @@ __global__ void __launch_bounds__(VS_NT) vs_plan_kernel(const VsPlanArgs a)
     const double jit2 = __dmul_rn(2.0, jit), shm2 = __dmul_rn(2.0, shm);
     const double P2 = __dmul_rn(2.0, (double)P), amp2 = __dmul_rn(2.0, (double)st.amp);
     const double Kbase = (double)st.K, kv2 = (double)__fmul_rn(2.0f, st.Kvar);
-    const double *ct = a.costab + st.cos_off;      /* c[0..T2), then h[0..T2) = 0.5*(1-c) */
-    const double *ht = ct + T2;
+    const double *ht = a.costab + st.cos_off;      /* h[0..T2) = 0.5*(1-c), then c[0..T2) */
+    const double *ct = ht + T2;
     const int DCi = (int)ceilf(st.DC);             /* (float)x < DC  <=>  x < ceil(DC) for integer x */
     const int DCs = st.DCs;
 
@@ -367,7 +373,7 @@ __device__ __forceinline__ int vs_quant_fast_nocheck(double v)
  * is worked by one CONSUMER warp (F phase; warps 0..NP-1, one per SM sub-partition) and VS_PW
  * PRODUCER warps (G and W phases) over two tiles; in flow mode by a single warp doing G then W.   */
 #define VS_NP        4
-#define VS_PW        3
+#define VS_PW        5
 #define VS_MAXSEG    4                     /* period segments a row can queue per bookkeeping pass */
 #define VS_TILE_I16  (32 * VS_TS)
 #define VS_THREADS_PAIRED ((VS_NP + VS_NP * VS_PW) * 32)
@@ -385,7 +391,9 @@ struct __align__(16) VsSeg {
 #define VS_SMEM_LANES (VS_NP * 32 * (int)sizeof(VsLane))
 #define VS_SMEM_SEGS  (VS_NP * 32 * VS_MAXSEG * (int)sizeof(VsSeg))
 #define VS_SMEM_NSEG  (VS_NP * 32 * 4)
-#define VS_SMEM_BASE(NTILE) (VS_SMEM_TILES(NTILE) + VS_SMEM_LANES + VS_SMEM_SEGS + VS_SMEM_NSEG)
+#define VS_ITEMS_BYTES (((32 * VS_MAXSEG * 7 + 4) * 2 + 15) & ~15)      /* work-item list of one producer warp */
+#define VS_SMEM_ITEMS(NPROD) (VS_NP * (NPROD) * VS_ITEMS_BYTES)
+#define VS_SMEM_BASE(NTILE) (VS_SMEM_TILES(NTILE) + VS_SMEM_LANES + VS_SMEM_SEGS + VS_SMEM_NSEG + VS_SMEM_ITEMS((NTILE) == 2 ? VS_PW : 1))
 /* noise: RNG states [31][VS_NT] words + the window's noise samples [NP][32][VS_WIN] int16 */
 #define VS_SMEM_NOISE (VS_RNG_DEG * VS_NT * 4 + VS_NP * 32 * VS_WIN * 2)
 
@@ -415,11 +423,17 @@ __device__ __forceinline__ void vs_draw_window(const VsLane &me, int w, VsRng &g
  * Given the period table a sample depends only on its index.  Closed phase = DC: a word fill.  The
  * open phase of a period (rising then falling branch, flowgen_shimmer.c:318-332) is one contiguous
  * index run.  Bookkeeping is lane-parallel (lane l <-> row row0 + l*step): each lane walks its row's
- * period table and queues segment descriptors in shared memory; then the warp evaluates every queued
- * run cooperatively, 32 consecutive samples per step, rising and falling through one code path. */
+ * period table, queues segment descriptors in shared memory and expands them into a flat list of
+ * work items (one item = 32 consecutive open-phase samples of one segment).  The warp then evaluates
+ * four items per step, straight-line, so that four table loads and FP64 chains are in flight. */
+#define VS_ITEM(row, seg, grp) ((uint16_t)((row) | ((seg) << 5) | ((grp) << 7)))
+#define VS_NULL_ITEM VS_ITEM(0, 0, 7)          /* group 7 starts at a0+224 > any window: evaluates nothing */
+#define VS_MAXITEMS (32 * VS_MAXSEG * 7 + 4)
+
 template <int MODE, bool NOISE>
-__device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, VsSeg *segs, int *nsegs, int w, int lane,
-                                            int row0, int step, const VsLane &mine, uint32_t &q, const int16_t *noisebuf)
+__device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, VsSeg *segs, int *nsegs, uint16_t *items,
+                                            int w, int lane, int row0, int step, const VsLane &mine, uint32_t &q,
+                                            const int16_t *noisebuf)
 {
     const int myrow = row0 + lane * step;
     const bool have_row = myrow < 32;
@@ -464,7 +478,8 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
     const int glo = max(wb_m, mine.nstart), ghi = min(wb_m + VS_WIN, mine.hi);
     bool pending = have_row && wb_m < mine.hi;
     while (__any_sync(VS_FULL, pending)) {
-        int n = 0;
+        int n = 0, ngrp = 0;
+        uint32_t grp_counts = 0;                              /* 4 bits per segment */
         if (pending) {
             VsSeg *my = segs + myrow * VS_MAXSEG;
             const int open_end = 2 * mine.T2;
@@ -474,11 +489,16 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
                 const int pend = e.start + e.T;
                 if (pend > glo) {
                     const int a0 = max(0, glo - e.start), a1 = min(e.T, ghi - e.start);
-                    if (a0 < min(a1, open_end) || (NOISE && mine.noise)) {
+                    const int nopen = min(a1, open_end) - a0;
+                    if (nopen > 0 || (NOISE && mine.noise)) {
                         VsSeg sg;
                         sg.Ad = e.Ad; sg.Kd = e.Kd; sg.rel = e.start - wb_m; sg.a0 = a0; sg.a1 = a1;
                         sg.T34 = (uint32_t)e.T3 | ((uint32_t)e.T4 << 16);
-                        my[n++] = sg;
+                        my[n] = sg;
+                        const int gcnt = nopen > 0 ? (nopen + 31) >> 5 : 0;
+                        grp_counts |= (uint32_t)gcnt << (4 * n);
+                        ngrp += gcnt;
+                        n++;
                     }
                 }
                 if (pend >= ghi) {                       /* window covered: q -> period of the next window's first sample */
@@ -489,30 +509,52 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
                 q++;
             }
         }
-        if (have_row) nsegs[myrow] = n;
+        if (NOISE && have_row) nsegs[myrow] = n;
+        /* flat work list: exclusive prefix sum of the per-row group counts */
+        int incl = ngrp;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(VS_FULL, incl, o);
+            if (lane >= o) incl += up;
+        }
+        const int total = __shfl_sync(VS_FULL, incl, 31);
+        {
+            int pos = incl - ngrp;
+            for (int sidx = 0; sidx < n; sidx++) {
+                const int gcnt = (int)((grp_counts >> (4 * sidx)) & 15u);
+                for (int gi = 0; gi < gcnt; gi++) items[pos++] = VS_ITEM(myrow, sidx, gi);
+            }
+            if (lane < 4) items[total + lane] = VS_NULL_ITEM;       /* pad to a multiple of 4 */
+        }
         __syncwarp();
 
-        for (int j = row0; j < 32; j += step) {
-            const int cnt = nsegs[j];
-            if (cnt == 0) continue;
-            const VsLane L = lanes[j];
-            int16_t *trow = tile + j * VS_TS;
-            const int T2 = L.T2, DCi = L.DCi;
-            const double *ct = L.ct;
-            for (int sidx = 0; sidx < cnt; sidx++) {
-                const VsSeg sg = segs[j * VS_MAXSEG + sidx];
+        for (int b = 0; b < total; b += 4) {
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int it = items[b + r];
+                const int row = it & 31;
+                const VsSeg sg = segs[row * VS_MAXSEG + ((it >> 5) & 3)];
+                const int T2 = lanes[row].T2, DCi = lanes[row].DCi;
+                const double *tab = lanes[row].ct;                  /* h[0..T2) then c[0..T2) */
                 const int o1 = min(sg.a1, 2 * T2);
-                for (int i = sg.a0 + lane; i < o1; i += 32) {
-                    const bool rising = i < T2;
-                    const double tv = __ldg(ct + (rising ? i + T2 : i - T2));      /* h[i] or c[i-T2] */
-                    const double fall = __dadd_rn(__dsub_rn(__dmul_rn(sg.Kd, tv), sg.Kd), 1.0);
-                    const int v = vs_ceil_s16(__dmul_rn(sg.Ad, rising ? tv : fall));
-                    if (v >= DCi) trow[sg.rel + i] = (int16_t)v;
-                }
-                if (NOISE && L.noise) {                                             /* :385-406 */
-                    __syncwarp();
+                const int i = sg.a0 + (it >> 7) * 32 + lane;
+                const double tv = __ldg(tab + min(i, 2 * T2 - 1));
+                const double fall = __dadd_rn(__dsub_rn(__dmul_rn(sg.Kd, tv), sg.Kd), 1.0);
+                const int v = vs_ceil_s16(__dmul_rn(sg.Ad, i < T2 ? tv : fall));
+                if (i < o1 && v >= DCi) tile[row * VS_TS + sg.rel + i] = (int16_t)v;
+            }
+        }
+
+        if (NOISE) {                                                /* :385-406 */
+            __syncwarp();
+            for (int j = row0; j < 32; j += step) {
+                if (!lanes[j].noise) continue;
+                const int cnt = nsegs[j];
+                int16_t *trow = tile + j * VS_TS;
+                const int16_t *nrow = noisebuf + j * VS_WIN;
+                for (int sidx = 0; sidx < cnt; sidx++) {
+                    const VsSeg sg = segs[j * VS_MAXSEG + sidx];
                     const int T3 = (int)(sg.T34 & 0xffffu), T4 = (int)(sg.T34 >> 16);
-                    const int16_t *nrow = noisebuf + j * VS_WIN;
                     for (int i = sg.a0 + lane; i < sg.a1; i += 32)
                         if (i < T4 || i >= T3)
                             trow[sg.rel + i] = (int16_t)vs_add_clip(trow[sg.rel + i], nrow[sg.rel + i]);
@@ -548,7 +590,7 @@ __device__ __forceinline__ void vs_write_row(const int16_t *trow, const VsLane &
 
 /* ---- F: one lane, one row, VS_WIN samples of the order-22 recurrence, in place ---------------------- */
 template <bool EXACT, bool RAW, bool CHECKED>
-__device__ __forceinline__ void vs_filter_window(uint32_t *row32, double (&y)[VS_RING], const double (&cf)[VS_ORDER + 1],
+__device__ __forceinline__ void vs_filter_window(uint32_t *row32, double (&y)[VS_RING], const double (&cf)[VS_RING],
                                                  double gaind, double pred, double *rrow, int wb, int lo, int hi)
 {
 #pragma unroll 1
@@ -567,12 +609,12 @@ __device__ __forceinline__ void vs_filter_window(uint32_t *row32, double (&y)[VS
                 if (EXACT) {
 #pragma unroll
                     for (int j = 1; j <= VS_ORDER; j++)               /* :279-281, same order */
-                        acc = __dsub_rn(acc, __dmul_rn(cf[j], y[(k + VS_RING - j) % VS_RING]));
+                        acc = __dsub_rn(acc, __dmul_rn(-cf[j], y[(k + VS_RING - j) % VS_RING]));
                     v = __dsub_rn(acc, __dmul_rn(pred, y[(k + VS_RING - 1) % VS_RING]));   /* :284 */
                 } else {
 #pragma unroll
-                    for (int j = VS_ORDER; j >= 1; j--)               /* oldest tap first */
-                        acc = __fma_rn(-cf[j], y[(k + VS_RING - j) % VS_RING], acc);
+                    for (int j = VS_ORDER; j >= 1; j--)               /* oldest tap first; cf = -A[j] */
+                        acc = __fma_rn(y[(k + VS_RING - j) % VS_RING], cf[j], acc);
                     v = __fma_rn(-pred, y[(k + VS_RING - 1) % VS_RING], acc);
                 }
                 y[k] = acc;                                           /* :287-289 (ring) */
@@ -602,6 +644,7 @@ vs_render_kernel(const VsRenderArgs a)
     VsLane *s_lanes = reinterpret_cast<VsLane *>(s_raw + VS_SMEM_TILES(NTILE));
     VsSeg *s_segs = reinterpret_cast<VsSeg *>(s_raw + VS_SMEM_TILES(NTILE) + VS_SMEM_LANES);
     int *s_nseg = reinterpret_cast<int *>(s_raw + VS_SMEM_TILES(NTILE) + VS_SMEM_LANES + VS_SMEM_SEGS);
+    unsigned char *s_items = s_raw + VS_SMEM_TILES(NTILE) + VS_SMEM_LANES + VS_SMEM_SEGS + VS_SMEM_NSEG;
     uint32_t *s_rng = reinterpret_cast<uint32_t *>(s_raw + VS_SMEM_BASE(NTILE));
     int16_t *s_noise = reinterpret_cast<int16_t *>(s_raw + VS_SMEM_BASE(NTILE) + VS_RNG_DEG * VS_NT * 4);
 
@@ -615,23 +658,23 @@ vs_render_kernel(const VsRenderArgs a)
     VsSeg *segs = s_segs + pair * 32 * VS_MAXSEG;
     int *nsegs = s_nseg + pair * 32;
     int16_t *noisebuf = s_noise + pair * 32 * VS_WIN;
+    uint16_t *items = reinterpret_cast<uint16_t *>(s_items + (pair * (PAIRED ? VS_PW : 1) + (prod > 0 ? prod : 0)) * VS_ITEMS_BYTES);
     const int group_threads = (1 + VS_PW) * 32;
 
     /* Row of this lane.  Consumer lane l filters row l; producer lane l keeps the books of row
      * prod + l*step (and, with noise, owns that row's RNG). */
     const int myrow = consumer ? lane : prod + lane * step;
     const uint32_t t = blockIdx.x * VS_NT + pair * 32 + (uint32_t)myrow;
-    const bool active = myrow < 32 && t < a.n_chunks;
+    uint32_t chunk_id = (myrow < 32 && t < a.n_rows) ? a.order[t] : VS_NO_CHUNK;
+    const bool active = chunk_id != VS_NO_CHUNK;
 
-    uint32_t q = 0, chunk_id = 0;
-    int preset = 0;
+    uint32_t q = 0;
     double gaind = 0.0, pred = 0.0;
     double *rrow = nullptr;
     VsLane me;
     me.tab = nullptr; me.ct = nullptr; me.orow = nullptr; me.fin = nullptr;
     me.nstart = 0; me.lo = 0; me.hi = 0; me.blk0 = 0; me.T2 = 0; me.DCi = 0; me.DCs = 0; me.noise = 0;
     if (active) {
-        chunk_id = a.order ? a.order[t] : t;
         const VsChunk ck = a.chunks[chunk_id];
         const VsStream st = a.streams[ck.stream];
         me.orow = a.pcm_out + st.out_off;
@@ -651,7 +694,7 @@ vs_render_kernel(const VsRenderArgs a)
         }
         const int phase = (int)((reinterpret_cast<uintptr_t>(me.orow) >> 1) & 7);
         me.blk0 = me.nstart - ((phase + me.nstart) & 7);
-        preset = st.preset; gaind = (double)st.gain; pred = (double)st.pre;
+        gaind = (double)st.gain; pred = (double)st.pre;
         rrow = (RAW && a.raw_out) ? a.raw_out + st.out_off : nullptr;
     }
     /* windows to run: max over the 32 rows of the group (each warp of the group sees a subset) */
@@ -678,7 +721,7 @@ vs_render_kernel(const VsRenderArgs a)
         __syncwarp();
         for (int w = 0; w < nwin; w++) {
             if (DRAWS) { if (active) vs_draw_window(me, w, g, re, rq, mynoise); __syncwarp(); }
-            vs_gen_tile<MODE, NOISE>(tile0, lanes, segs, nsegs, w, lane, 0, 1, me, q, noisebuf);
+            vs_gen_tile<MODE, NOISE>(tile0, lanes, segs, nsegs, items, w, lane, 0, 1, me, q, noisebuf);
             __syncwarp();
             for (int j = 0; j < 32; j++) vs_write_row(tile0 + j * VS_TS, lanes[j], w, lane);
             __syncwarp();
@@ -696,24 +739,22 @@ vs_render_kernel(const VsRenderArgs a)
     }
     if (consumer) {
         double y[VS_RING];
-        double cf[VS_ORDER + 1];
 #pragma unroll
         for (int j = 0; j < VS_RING; j++) y[j] = 0.0;
-#pragma unroll
-        for (int j = 0; j <= VS_ORDER; j++) cf[j] = __ldg(a.coef + preset * VS_RING + j);
+
         vs_named_barrier(1 + pair, group_threads);           /* window 0 generated */
         for (int w = 0; w < nwin; w++) {
             const int wb = me.blk0 + w * VS_WIN;
             if (active && wb < me.hi)
                 vs_filter_window<EXACT, RAW, CHECKED>(
-                    reinterpret_cast<uint32_t *>(tile0 + (w & 1) * VS_TILE_I16 + lane * VS_TS), y, cf, gaind, pred, rrow,
+                    reinterpret_cast<uint32_t *>(tile0 + (w & 1) * VS_TILE_I16 + lane * VS_TS), y, a.ncf, gaind, pred, rrow,
                     wb, me.lo, me.hi);
             vs_named_barrier(1 + pair, group_threads);
         }
     } else {
         if (DRAWS && active) vs_draw_window(me, 0, g, re, rq, mynoise);
         __syncwarp();
-        vs_gen_tile<MODE, NOISE>(tile0, lanes, segs, nsegs, 0, lane, prod, step, me, q, noisebuf);
+        vs_gen_tile<MODE, NOISE>(tile0, lanes, segs, nsegs, items, 0, lane, prod, step, me, q, noisebuf);
         vs_named_barrier(1 + pair, group_threads);           /* window 0 generated */
         for (int w = 0; w < nwin; w++) {
             int16_t *other = tile0 + ((w + 1) & 1) * VS_TILE_I16;
@@ -722,7 +763,7 @@ vs_render_kernel(const VsRenderArgs a)
             if (w + 1 < nwin) {
                 if (DRAWS && active) vs_draw_window(me, w + 1, g, re, rq, mynoise);
                 __syncwarp();
-                vs_gen_tile<MODE, NOISE>(other, lanes, segs, nsegs, w + 1, lane, prod, step, me, q, noisebuf);
+                vs_gen_tile<MODE, NOISE>(other, lanes, segs, nsegs, items, w + 1, lane, prod, step, me, q, noisebuf);
             }
             vs_named_barrier(1 + pair, group_threads);
         }
@@ -768,7 +809,7 @@ cudaError_t vs_launch_plan(const VsPlanArgs &a, bool want_log, cudaStream_t s)
 template <int MODE, bool NOISE, int FLAGS>
 static void vs_go(const VsRenderArgs &a, cudaStream_t s)
 {
-    const unsigned grid = (a.n_chunks + VS_NT - 1) / VS_NT;
+    const unsigned grid = a.n_rows / VS_NT;
     const int dyn = VS_SMEM_BASE(MODE == VS_MODE_FLOW ? 1 : 2) + ((NOISE && MODE != VS_MODE_FILTER) ? VS_SMEM_NOISE : 0);
     cudaFuncSetAttribute(vs_render_kernel<MODE, NOISE, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     vs_render_kernel<MODE, NOISE, FLAGS><<<grid, MODE == VS_MODE_FLOW ? VS_NT : VS_THREADS_PAIRED, dyn, s>>>(a);
