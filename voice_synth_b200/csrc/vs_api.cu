@@ -360,6 +360,54 @@ uint32_t choose_chunk(vs_ctx *ctx, const Slot &slot, int mode, size_t n_streams,
     return best_L;
 }
 
+/* Per-stream chunk counts for the filtering modes.  A chunk of stream s costs  W_s + L_s  sample
+ * steps (W_s = carry warm-up of its preset); the kernel time is that of the most expensive chunk
+ * times the number of waves, one wave = one CTA of VS_NT rows per SM.  So: give every stream the
+ * chunk length  L_s = budget - W_s  and pick the smallest budget whose rows fit in `waves` waves;
+ * take the wave count with the smallest  waves * budget. */
+void plan_filter_chunks(vs_ctx *ctx, const Slot &slot, const std::vector<VsStream> &hs, size_t a0, size_t a1,
+                        std::vector<uint32_t> &nchunks)
+{
+    const size_t ns = a1 - a0;
+    nchunks.assign(ns, 1u);
+    if (ctx->opt_chunk < 0 || ctx->opt_exact) return;
+    if (ctx->opt_chunk > 0) {
+        uint32_t L = ((uint32_t)ctx->opt_chunk + 7u) & ~7u;
+        if (L < 64) L = 64;
+        for (size_t i = 0; i < ns; i++) nchunks[i] = hs[a0 + i].n <= L ? 1u : (uint32_t)((hs[a0 + i].n + L - 1) / L);
+        return;
+    }
+    const double cap = (double)slot.sm_count * VS_NT;          /* rows per wave */
+    uint32_t nmax = 0;
+    for (size_t i = 0; i < ns; i++) nmax = std::max(nmax, hs[a0 + i].n);
+    auto rows_for = [&](double budget, std::vector<uint32_t> *out) -> double {
+        double rows = 0;
+        for (size_t i = 0; i < ns; i++) {
+            const VsStream &s = hs[a0 + i];
+            uint32_t C = 1;
+            if ((double)s.n > budget) {
+                const double L = std::max(512.0, budget - (double)ctx->warm[s.preset]);
+                C = (uint32_t)std::ceil((double)s.n / L);
+            }
+            if (out) (*out)[i] = C;
+            rows += C;
+        }
+        return rows;
+    };
+    double best_cost = 1e300, best_budget = (double)nmax;
+    for (int waves = 1; waves <= 8; waves++) {
+        if (rows_for((double)nmax, nullptr) > waves * cap) continue;          /* even unchunked does not fit */
+        double lo = 512.0, hi = (double)nmax;                                  /* smallest budget that fits */
+        for (int it = 0; it < 40; it++) {
+            const double mid = 0.5 * (lo + hi);
+            if (rows_for(mid, nullptr) <= waves * cap * 0.97) hi = mid; else lo = mid;   /* 3 % room for preset padding */
+        }
+        const double cost = waves * hi;
+        if (cost < best_cost * 0.98) { best_cost = cost; best_budget = hi; }
+    }
+    rows_for(best_budget, &nchunks);
+}
+
 int run_batch(vs_ctx *ctx, const Batch &b)
 {
     if (!ctx) return VS_EINVAL;
@@ -480,7 +528,10 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             uint64_t tot = 0;
             double wsum = 0.0;
             for (size_t i = a0; i < a1; i++) { tot += hs[i].n; if (b.mode != VS_MODE_FLOW) wsum += ctx->warm[hs[i].preset]; }
-            const uint32_t L = choose_chunk(ctx, sl, b.mode, a1 - a0, tot, wsum / (double)(a1 - a0));
+            const uint32_t Lflow = b.mode == VS_MODE_FLOW ? choose_chunk(ctx, sl, b.mode, a1 - a0, tot, 0.0) : 0u;
+            std::vector<uint32_t> nch;
+            if (b.mode != VS_MODE_FLOW) plan_filter_chunks(ctx, sl, hs, a0, a1, nch);
+            (void)wsum;
             slab_c0[k] = hc.size();
             for (size_t i = a0; i < a1; i++) {
                 VsStream &s = hs[i];
@@ -488,7 +539,15 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 /* host outputs are mirrored on the device at the same offsets relative to a 16-byte
                  * aligned slab base, so the phase of a row is its sample offset mod 8 either way */
                 const uint32_t ph = (uint32_t)(base_addr & 7);
-                const uint32_t C = (L == 0 || s.n <= L) ? 1u : (uint32_t)((s.n + L - 1) / L);
+                uint32_t C, L;
+                if (b.mode == VS_MODE_FLOW) {
+                    L = Lflow;
+                    C = (L == 0 || s.n <= L) ? 1u : (uint32_t)((s.n + L - 1) / L);
+                } else {
+                    C = nch[i - a0];
+                    L = C <= 1 ? 0u : (uint32_t)(((s.n + C - 1) / C + 7u) & ~7u);     /* equal chunks, multiple of 8 */
+                    if (C > 1) C = (uint32_t)((s.n + L - 1) / L);
+                }
                 s.chunk0 = (uint32_t)hc.size();
                 s.n_chunks = C;
                 s.tab_off = tab_total;
