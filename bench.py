@@ -1,0 +1,320 @@
+#!/usr/bin/env python3
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config, on 1..8 B200 of one node.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                      (the reference's own CPU tools, all host cores)
+
+metric   synthesized samples/sec (Msamples/s); % of HBM-write roofline   (BASELINE.json:metric)
+workload configs[1]: batch of 4096 streams x 1 s covering every vowel preset, fused flowgen+vowel
+         kernel (vs_synth_batch).  With N GPUs every rank synthesises its own 4096 streams (weak
+         scaling: streams are independent, no collective on the data path -- SURVEY.md 8e).
+step     one vs_synth_batch call over the rank's whole batch.
+value    kernel path, PCM left resident in HBM (device output buffer, 180 MB per step > 126 MB L2).
+e2e      the same call with a pinned HOST output buffer: parameter/descriptor H2D and the PCM D2H
+         over PCIe are inside the timed region.
+The line also carries the dominant kernel's roofline (HBM-write as BASELINE asks, plus the FP64 pipe
+that actually binds it) and the reference CPU tools timed on this box's cores (cpu_baseline).
+"""
+import argparse
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "synthesized samples/sec (Msamples/s); % of HBM-write roofline"
+N_STREAMS = 4096
+FP64_INSTR_PER_SAMPLE = 25          # 1 mul + 22 FMA + pre-emphasis FMA + quantiser add
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the unmodified reference tools (oracle/_ref), one process per core
+# ------------------------------------------------------------------------------------------------
+def _ref_tools():
+    ref = ROOT / "oracle" / "_ref"
+    if all((ref / f).exists() for f in ("flowgen_shimmer", "vowel", "timeshim.so")):
+        return ref
+    return None
+
+
+def _run_ref_stream(job):
+    ref, tmpdir, idx, fargs, preset, seed = job
+    env = dict(os.environ, VS_SEED=str(seed), LD_PRELOAD=str(ref / "timeshim.so"))
+    f = os.path.join(tmpdir, f"f{idx}.wav")
+    o = os.path.join(tmpdir, f"o{idx}.wav")
+    subprocess.run([str(ref / "flowgen_shimmer"), "-o", f] + fargs, env=env, stdout=subprocess.DEVNULL, check=True)
+    subprocess.run([str(ref / "vowel"), "-i", f, "-o", o, "-v", preset], env=env, stdout=subprocess.DEVNULL, check=True)
+    n = (os.path.getsize(o) - 72) // 2
+    os.unlink(f)
+    os.unlink(o)
+    return n
+
+
+def _run_port_stream(job):
+    from oracle import pyoracle as O
+    _, _, idx, fargs, preset, seed = job
+    par = O.flow_par_from_cli(["-o", "x"] + fargs, seed)
+    return int(O.vowel(O.flowgen(par), preset).size)
+
+
+def cpu_reference_throughput(n_streams, first=0):
+    """Msamples/s of the reference CPU pipeline over `n_streams` streams of the bench workload."""
+    from voice_synth_b200 import workloads
+    p, f = workloads.cfg2(n=N_STREAMS)
+    ref = _ref_tools()
+    cores = os.cpu_count() or 1
+    tmpdir = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    jobs = [(ref, tmpdir, i, workloads.cli_args(p, i % N_STREAMS), chr(f.preset[i % N_STREAMS]), int(p.seed[i % N_STREAMS]))
+            for i in range(first, first + n_streams)]
+    fn = _run_ref_stream if ref else _run_port_stream
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        total = sum(ex.map(fn, jobs, chunksize=4))
+    dt = time.perf_counter() - t0
+    try:
+        os.rmdir(tmpdir)
+    except OSError:
+        pass
+    return total / dt / 1e6, cores, ("reference" if ref else "port"), dt, total
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    per_step = args.ref_streams
+    vals = []
+    for it in range(args.warmup + args.steps):
+        v, cores, kind, dt, total = cpu_reference_throughput(per_step, first=it * per_step)
+        if it >= args.warmup:
+            vals.append((v, dt))
+    value = sum(v for v, _ in vals) / len(vals)
+    ms = 1e3 * sum(d for _, d in vals) / len(vals)
+    sample = (f"{per_step} of the workload's {N_STREAMS} streams per step: flowgen_shimmer -> tmpfs WAV -> vowel, "
+              f"{'unmodified reference tools built with the Makefile flags (-O0)' if kind == 'reference' else 'oracle port'}, "
+              f"one process per core")
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "Msamples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg2: 4096 streams x 1 s x 10 vowel presets (bounded sample per step)",
+                       "streams_per_step": per_step},
+            "cpu_baseline": {"value": round(value, 3), "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": round(value, 3), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 8 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 8 and r[2].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        # the busy samples are the upper half (the sampler also sees idle gaps between steps)
+        busy = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    p = ROOT / "profiles" / "ncu_summary.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get("render_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-streams", type=int, default=1024, help="streams per step of the reference arm")
+    ap.add_argument("--cpu-sample", type=int, default=2048, help="streams of the cpu_baseline sample (0 = skip)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from voice_synth_b200 import api, workloads
+
+    if args.warmup < 3:
+        args.warmup = 3
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # the rank's share of the job: its own 4096 streams (distinct seeds), nothing is exchanged
+    p, f = workloads.cfg2(n=N_STREAMS)
+    p.seed[...] = (1000 + rank * N_STREAMS + np.arange(N_STREAMS)).astype(np.uint32)
+    ns = api.flow_nsamples(p)
+    samples_per_step = int(ns.sum())
+
+    stream = torch.cuda.current_stream()
+    ctx = api.Context(devices=[local_rank], stream=stream.cuda_stream)
+    dev_out = torch.empty(samples_per_step, dtype=torch.int16, device="cuda")
+    host_out_t = torch.empty(samples_per_step, dtype=torch.int16).pin_memory()
+    host_out = host_out_t.numpy()
+
+    def step_device():
+        ctx.synth_batch(p, f, out=dev_out)
+
+    def step_host():
+        ctx.synth_batch(p, f, out=host_out)
+
+    # ---- value: device-resident ----------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    ctx.sync()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    render_ms, plan_ms, launches, warm = [], [], 0, 0
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+        t = ctx.timing()                 # syncs the ctx: reads this step's CUDA-event durations
+        render_ms.append(t["render_ms"])
+        plan_ms.append(t["plan_ms"])
+        launches += t["launches"]
+        warm = t["warmup_samples"]
+    e1.record(stream)
+    barrier()
+    dev_ms = e0.elapsed_time(e1) / args.steps
+
+    # ---- e2e: pinned host output, PCIe inside the timed region -------------------------------------
+    for _ in range(3):
+        step_host()
+    barrier()
+    h2d = d2h = 0
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for _ in range(args.steps):
+        step_host()                      # returns when the PCM has landed in host memory
+        t = ctx.timing()
+        h2d, d2h = t["h2d_bytes"], t["d2h_bytes"]
+        launches += t["launches"]
+    e3.record(stream)
+    barrier()
+    e2e_ms = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3) / args.steps
+    clocks = sampler.stop()
+
+    fp64_tflops, fp64_mhz = ctx.fp64_peak()
+
+    # max over ranks
+    times = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(times[0]), float(times[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_samples = samples_per_step * world
+    value = total_samples / (dev_ms * 1e-3) / 1e6
+    e2e = total_samples / (e2e_ms * 1e-3) / 1e6
+    peak, peak_src = measured_peaks()
+    r_ms = float(np.mean(render_ms))
+    achieved = 2.0 * samples_per_step / (r_ms * 1e-3) / 1e9            # algorithmic bytes: 2 B per output sample
+    dfma_rate = FP64_INSTR_PER_SAMPLE * (samples_per_step + warm) / (r_ms * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(dev_ms, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg2: 4096 streams x 1 s (22050 samples) per GPU, presets a,i,u,1..7 round-robin, F0 80-237.5 Hz, "
+                               "jitter 0-3.5 %, shimmer 0-7.5 %, fused vs_synth_batch",
+                   "streams_per_gpu": N_STREAMS, "samples_per_step_per_gpu": samples_per_step,
+                   "l2": "output 180.6 MB per step > 126 MB L2, rewritten every step",
+                   "plan_ms": round(float(np.mean(plan_ms)), 4), "render_ms": round(r_ms, 4)},
+        "e2e": {"value": round(e2e, 1), "unit": "Msamples/s", "ms_per_step": round(e2e_ms, 3),
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "vs_render_kernel<SYNTH> (10 per-preset launches per step)", "achieved": round(achieved, 1),
+                     "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": ncu_traffic(), "peak_source": peak_src,
+                     "note": "the FP64 recurrence, not HBM, binds this kernel (SURVEY.md 8d): see fp64",
+                     "fp64": {"achieved_tdfma_s": round(dfma_rate, 3), "peak_tdfma_s": round(fp64_tflops / 2, 3),
+                              "frac": round(dfma_rate / (fp64_tflops / 2), 4), "dfma_per_sample": FP64_INSTR_PER_SAMPLE,
+                              "counts": "useful + carry warm-up samples", "peak_source": "vs_measure_fp64_peak on this GPU",
+                              "implied_sm_mhz": round(fp64_mhz)}},
+        "clocks": clocks,
+    }
+    if world == 1 and args.cpu_sample > 0:
+        try:
+            v, cores, kind, dt, total = cpu_reference_throughput(args.cpu_sample)
+            line["cpu_baseline"] = {"value": round(v, 3), "unit": "Msamples/s", "cores": cores, "kind": kind,
+                                    "sample": f"{args.cpu_sample} of the {N_STREAMS} streams ({total} samples, {dt:.1f} s wall): "
+                                              "flowgen_shimmer -> tmpfs WAV -> vowel, one process per core, Makefile flags (-O0)"}
+        except Exception as ex:  # the baseline is a report, never a reason to lose the GPU numbers
+            line["cpu_baseline"] = {"value": None, "unit": "Msamples/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -16,9 +16,10 @@
  *     DEVICE memory of the ctx's device (detected with cudaPointerGetAttributes; device pointers
  *     need a single-device ctx).  Parameter arrays are always host memory;
  *   - all stream positions ("offsets") are in SAMPLES relative to the buffer pointer;
- *   - work is enqueued on the ctx's CUDA streams.  Calls whose buffers are all device or pinned
- *     return after enqueueing; call vs_sync() before touching the results.  Calls with pageable
- *     host buffers stage through ctx-owned pinned memory and return when the data has landed;
+ *   - work is enqueued on the ctx's CUDA streams.  Calls whose I/O buffers are DEVICE memory return
+ *     after enqueueing; call vs_sync() before touching the results (and to learn about device-side
+ *     errors).  Calls with HOST buffers return when the data has landed (PCM travels over PCIe on
+ *     a side stream, slab by slab, while the next slab renders; pinned buffers avoid staging);
  *   - there is NO CPU fallback: without a usable sm_100 device vs_ctx_create() fails.
  *
  * Arithmetic contract (tests/): pitch periods, amplitudes, pulse boundaries, random() draws and
@@ -109,6 +110,8 @@ typedef struct vs_timing {
     uint32_t chunks;          /* time-chunks the streams were split into                 */
     uint64_t samples;         /* output samples produced                                 */
     uint64_t warmup_samples;  /* extra samples filtered only to settle chunk carries     */
+    uint64_t h2d_bytes;       /* host->device bytes the call copied (descriptors, tables, flow_in) */
+    uint64_t d2h_bytes;       /* device->host bytes the call copied (PCM, raw, period log)         */
 } vs_timing;
 
 /* ---- options (vs_ctx_set_option) ------------------------------------------------------------ */

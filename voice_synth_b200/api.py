@@ -162,6 +162,8 @@ class FlowParams:
         q = FlowParams(len(idx))
         for name, _, _ in _FLOW_FIELDS:
             getattr(q, name)[...] = getattr(self, name)[idx]
+        if getattr(self, "meta", None):
+            q.meta = {k: (None if v is None else v[idx]) for k, v in self.meta.items()}
         return q
 
     def _c(self):

@@ -618,6 +618,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 /* tables only ever grow; a synchronous copy keeps the host vector free to grow again */
                 CU(cudaStreamSynchronize(sl.compute));
                 CU(cudaMemcpy(sl.costab.p, ctx->cos_host.data(), ctx->cos_host.size() * sizeof(double), cudaMemcpyHostToDevice));
+                ctx->timing.h2d_bytes += ctx->cos_host.size() * sizeof(double);
                 sl.costab_uploaded = ctx->cos_host.size();
             }
         }
@@ -688,6 +689,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         CU(cudaMemcpyAsync(sl.streams.p, sl.h_streams.p, ns * sizeof(VsStream), cudaMemcpyHostToDevice, sl.compute));
         CU(cudaMemcpyAsync(sl.chunks.p, sl.h_chunks.p, nc * sizeof(VsChunk), cudaMemcpyHostToDevice, sl.compute));
         CU(cudaMemcpyAsync(sl.order.p, sl.h_order.p, nrows * sizeof(uint32_t), cudaMemcpyHostToDevice, sl.compute));
+        ctx->timing.h2d_bytes += ns * sizeof(VsStream) + nc * sizeof(VsChunk) + nrows * sizeof(uint32_t);
         CU(cudaMemsetAsync(sl.status.p, 0, sizeof(int32_t), sl.compute));
 
         cudaEvent_t t_first = nullptr;
@@ -709,6 +711,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                     d_in = (const int16_t *)sl.flowin[d].p;
                     CU(cudaMemcpyAsync(sl.flowin[d].p, b.flow_in + geom[k].in_min, (geom[k].in_max - geom[k].in_min) * sizeof(int16_t),
                                        cudaMemcpyHostToDevice, sl.compute));
+                    ctx->timing.h2d_bytes += (geom[k].in_max - geom[k].in_min) * sizeof(int16_t);
                 }
             }
 
@@ -775,6 +778,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 /* merge rows that touch into runs: a dense batch is one copy per slab */
                 uint64_t run_lo = hs[a0].out_off, run_hi = hs[a0].out_off + hs[a0].n;
                 auto flush = [&](uint64_t lo, uint64_t hi) -> cudaError_t {
+                    ctx->timing.d2h_bytes += (hi - lo) * (sizeof(int16_t) + (b.raw_out ? sizeof(double) : 0));
                     cudaError_t e = cudaMemcpyAsync(b.pcm_out + lo, d_pcm + (lo - geom[k].out_min), (hi - lo) * sizeof(int16_t),
                                                     cudaMemcpyDeviceToHost, sl.copy);
                     if (e == cudaSuccess && b.raw_out)
@@ -790,6 +794,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 CU(cudaEventRecord(sl.slab_done[d], sl.copy));
             }
         }
+        if (want_log) ctx->timing.d2h_bytes += (log_hi - log_lo) * sizeof(vs_period_rec);
         if (want_log)
             CU(cudaMemcpyAsync(b.log->rec + log_lo, sl.log.p, (log_hi - log_lo) * sizeof(vs_period_rec), cudaMemcpyDeviceToHost, sl.compute));
         if (want_log && b.log->count)

@@ -29,6 +29,11 @@ def _finish(n, dur, F0, jit_pct, shm_pct, seed, snr_db=None, fs=22050):
         p.DC[on] = f32(0.25)                                                                     # -n sets par.DC = .25
         flags[on] |= VS_F_NOISE
     p.flags[...] = flags
+    # the decimal values a command line would carry (cli_args); the float32 fields above are what the
+    # reference's atof()/100 conversions make of them
+    p.meta = {"jit_pct": np.broadcast_to(np.asarray(jit_pct, dtype=np.float64), (n,)).copy(),
+              "shm_pct": np.broadcast_to(np.asarray(shm_pct, dtype=np.float64), (n,)).copy(),
+              "snr_db": None if snr_db is None else np.broadcast_to(np.asarray(snr_db, dtype=np.float64), (n,)).copy()}
     return p
 
 
@@ -88,13 +93,14 @@ def cfg5(n=1 << 20, first=0, dur=1.0):
 
 def cli_args(p, i):
     """the reference command line (without -o) that yields stream i of FlowParams p"""
+    m = p.meta
     a = ["-d", repr(float(p.dur[i])), "-f", repr(float(p.F0[i])), "-g", repr(max(125.0, float(p.F0[i]) + 5.0))]
     if p.flags[i] & VS_F_JITTER:
-        a += ["-j", repr(round(float(p.jitter[i]) * 100.0, 6))]
+        a += ["-j", repr(round(float(m["jit_pct"][i]), 6))]
     if p.flags[i] & VS_F_SHIMMER:
-        a += ["-s", repr(round(float(p.shimmer[i]) * 100.0, 6))]
+        a += ["-s", repr(round(float(m["shm_pct"][i]), 6))]
     if p.flags[i] & VS_F_NOISE:
-        a += ["-n", repr(round(10.0 * math.log10(float(p.noise[i])), 6))]
+        a += ["-n", repr(round(float(m["snr_db"][i]), 6))]
     if int(p.fs[i]) != 22050:
         a += ["-r", str(int(p.fs[i]))]
     return a
