@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <map>
 #include <string>
 #include <vector>
@@ -58,6 +59,16 @@ struct Slot {
     size_t costab_uploaded = 0;
     std::vector<cudaEvent_t> tev;                    /* timing events (slot 0 only) */
     size_t tev_used = 0;
+    unsigned scratch_parity = 0;                     /* which pcm[]/raw[]/flowin[] the next slab uses */
+    bool slab_done_valid[2] = {false, false};
+    /* chunk plan of the previous call, reused when the batch has the same shape */
+    std::vector<uint64_t> plan_sig;
+    std::vector<VsChunk> plan_chunks;
+    std::vector<uint32_t> plan_order, plan_nch;
+    struct PlanGroup { size_t r0, r1; int preset; };
+    std::vector<std::vector<PlanGroup>> plan_groups;
+    std::vector<size_t> plan_slab_c0, plan_slab_r0;
+    uint64_t plan_tab_total = 0, plan_warm_total = 0;
 };
 
 } // namespace
@@ -70,6 +81,7 @@ struct vs_ctx {
     int opt_slab = 0;
     double opt_warps = 2.0;
     int opt_long_scan = 1;
+    int opt_async_host = 0;
     std::vector<double> cos_host;
     std::map<int, uint32_t> cos_index;
     int warm[VS_NUM_PRESETS];    /* warm-up samples per preset at opt_tol (gain-independent part) */
@@ -378,38 +390,53 @@ void plan_filter_chunks(vs_ctx *ctx, const Slot &slot, const std::vector<VsStrea
         return;
     }
     const double cap = (double)slot.sm_count * VS_NT;          /* rows per wave */
+    /* streams of equal (length, preset) get equal chunk counts: plan over the distinct classes */
+    std::map<std::pair<uint32_t, uint8_t>, uint32_t> classes;
     uint32_t nmax = 0;
-    for (size_t i = 0; i < ns; i++) nmax = std::max(nmax, hs[a0 + i].n);
-    auto rows_for = [&](double budget, std::vector<uint32_t> *out) -> double {
+    for (size_t i = 0; i < ns; i++) {
+        classes[{hs[a0 + i].n, hs[a0 + i].preset}]++;
+        nmax = std::max(nmax, hs[a0 + i].n);
+    }
+    auto chunks_of = [&](uint32_t n, uint8_t preset, double budget) -> uint32_t {
+        if ((double)n <= budget) return 1u;
+        const double L = std::max(512.0, budget - (double)ctx->warm[preset]);
+        return (uint32_t)std::ceil((double)n / L);
+    };
+    auto rows_for = [&](double budget) -> double {
         double rows = 0;
-        for (size_t i = 0; i < ns; i++) {
-            const VsStream &s = hs[a0 + i];
-            uint32_t C = 1;
-            if ((double)s.n > budget) {
-                const double L = std::max(512.0, budget - (double)ctx->warm[s.preset]);
-                C = (uint32_t)std::ceil((double)s.n / L);
-            }
-            if (out) (*out)[i] = C;
-            rows += C;
-        }
+        for (const auto &kv : classes) rows += (double)kv.second * chunks_of(kv.first.first, kv.first.second, budget);
         return rows;
     };
     double best_cost = 1e300, best_budget = (double)nmax;
     for (int waves = 1; waves <= 8; waves++) {
-        if (rows_for((double)nmax, nullptr) > waves * cap) continue;          /* even unchunked does not fit */
+        if (rows_for((double)nmax) > waves * cap) continue;                    /* even unchunked does not fit */
         double lo = 512.0, hi = (double)nmax;                                  /* smallest budget that fits */
-        for (int it = 0; it < 40; it++) {
+        for (int it = 0; it < 30; it++) {
             const double mid = 0.5 * (lo + hi);
-            if (rows_for(mid, nullptr) <= waves * cap * 0.97) hi = mid; else lo = mid;   /* 3 % room for preset padding */
+            if (rows_for(mid) <= waves * cap * 0.97) hi = mid; else lo = mid;  /* 3 % room for preset padding */
         }
         const double cost = waves * hi;
         if (cost < best_cost * 0.98) { best_cost = cost; best_budget = hi; }
     }
-    rows_for(best_budget, &nchunks);
+    for (size_t i = 0; i < ns; i++) nchunks[i] = chunks_of(hs[a0 + i].n, hs[a0 + i].preset, best_budget);
 }
+
+struct HostProf {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    HostProf() : on(getenv("VS_PROFILE_HOST") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what)
+    {
+        if (!on) return;
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[vs host] %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t - t0).count());
+        t0 = t;
+    }
+};
 
 int run_batch(vs_ctx *ctx, const Batch &b)
 {
+    HostProf prof;
     if (!ctx) return VS_EINVAL;
     if (b.n == 0) return VS_OK;
     if (!b.pcm_out) return fail(ctx, VS_EINVAL, "pcm_out is NULL");
@@ -461,6 +488,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         if (want_log) hs[i].log_off = b.log->rec_offsets[i];
     }
 
+    prof.mark("stream descriptors");
     /* ---- 2. where do the buffers live ------------------------------------------------------- */
     int odev = -1;
     const PtrKind out_kind = classify(b.pcm_out, &odev);
@@ -511,27 +539,42 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         if (!out_dev) {
             if (ctx->opt_slab > 0) slab_streams = (size_t)ctx->opt_slab;
             else {
+                /* one slab per call unless the device mirror of the output would be huge; PCIe/compute
+                 * overlap comes from alternating two scratch buffers ACROSS calls (VS_OPT_ASYNC_HOST) */
                 const uint64_t bytes = total * 2;
-                size_t want = (size_t)std::min<uint64_t>(16, std::max<uint64_t>(1, bytes / (24ull << 20)));
+                size_t want = (size_t)std::max<uint64_t>(1, (bytes + (1ull << 30) - 1) >> 30);
                 slab_streams = (ns + want - 1) / want;
             }
             if (slab_streams < 1) slab_streams = 1;
         }
         const size_t n_slabs = (ns + slab_streams - 1) / slab_streams;
 
-        /* chunk plan */
-        std::vector<VsChunk> hc;
-        std::vector<size_t> slab_c0(n_slabs + 1, 0);
+        /* chunk plan + row order: a function of the batch SHAPE only (lengths, presets, row phases,
+         * options), so a call shaped like the previous one reuses it */
+        std::vector<uint64_t> sig;
+        sig.reserve(ns + 8);
+        sig.push_back(((uint64_t)b.mode << 48) ^ ((uint64_t)n_slabs << 24) ^ (uint64_t)slab_streams);
+        sig.push_back((uint64_t)(int64_t)ctx->opt_chunk ^ ((uint64_t)ctx->opt_exact << 62) ^ ((uint64_t)sl.sm_count << 40));
+        { double t = ctx->opt_tol, w = ctx->opt_warps; uint64_t u; memcpy(&u, &t, 8); sig.push_back(u); memcpy(&u, &w, 8); sig.push_back(u); }
+        for (size_t i = s0; i < s1; i++) {
+            const uint64_t base_addr = out_dev ? (reinterpret_cast<uintptr_t>(b.pcm_out) >> 1) + hs[i].out_off : hs[i].out_off;
+            sig.push_back((uint64_t)hs[i].n | ((uint64_t)hs[i].preset << 32) | ((base_addr & 7) << 40) | ((uint64_t)(hs[i].tab_cap & 0xfffffu) << 44));
+        }
+        const bool plan_hit = sig == sl.plan_sig;
+        if (!plan_hit) {
+        std::vector<VsChunk> &hc = sl.plan_chunks;
+        hc.clear();
+        sl.plan_nch.assign(ns, 1u);
+        std::vector<size_t> &slab_c0 = sl.plan_slab_c0;
+        slab_c0.assign(n_slabs + 1, 0);
         uint64_t tab_total = 0, warm_total = 0;
         for (size_t k = 0; k < n_slabs; k++) {
             const size_t a0 = s0 + k * slab_streams, a1 = std::min(s1, a0 + slab_streams);
             uint64_t tot = 0;
-            double wsum = 0.0;
-            for (size_t i = a0; i < a1; i++) { tot += hs[i].n; if (b.mode != VS_MODE_FLOW) wsum += ctx->warm[hs[i].preset]; }
+            for (size_t i = a0; i < a1; i++) tot += hs[i].n;
             const uint32_t Lflow = b.mode == VS_MODE_FLOW ? choose_chunk(ctx, sl, b.mode, a1 - a0, tot, 0.0) : 0u;
             std::vector<uint32_t> nch;
             if (b.mode != VS_MODE_FLOW) plan_filter_chunks(ctx, sl, hs, a0, a1, nch);
-            (void)wsum;
             slab_c0[k] = hc.size();
             for (size_t i = a0; i < a1; i++) {
                 VsStream &s = hs[i];
@@ -548,9 +591,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                     L = C <= 1 ? 0u : (uint32_t)(((s.n + C - 1) / C + 7u) & ~7u);     /* equal chunks, multiple of 8 */
                     if (C > 1) C = (uint32_t)((s.n + L - 1) / L);
                 }
-                s.chunk0 = (uint32_t)hc.size();
-                s.n_chunks = C;
-                s.tab_off = tab_total;
+                sl.plan_nch[i - s0] = C;
                 tab_total += s.tab_cap;
                 const uint32_t W = (b.mode == VS_MODE_FLOW) ? 0u : (uint32_t)ctx->warm[s.preset];
                 for (uint32_t c = 0; c < C; c++) {
@@ -566,17 +607,19 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             }
         }
         slab_c0[n_slabs] = hc.size();
-        const size_t nc = hc.size();
-        /* render rows: inside each slab the chunks are grouped by vowel preset (a CTA serves one
-         * preset, so its coefficients sit in uniform registers), longest first inside a preset (the
-         * 32 lanes of a warp then run a similar number of windows), and every preset group is padded
-         * to a whole CTA with VS_NO_CHUNK rows */
-        std::vector<uint32_t> order;
-        struct Group { size_t r0, r1; int preset; };             /* rows [r0,r1) of one preset = one launch */
-        std::vector<std::vector<Group>> slab_groups(n_slabs);
-        std::vector<size_t> slab_r0(n_slabs + 1, 0);
+        sl.plan_tab_total = tab_total;
+        sl.plan_warm_total = warm_total;
+        prof.mark("chunk plan");
+        /* render rows: inside each slab the chunks are grouped by vowel preset (one launch per preset:
+         * its coefficients are kernel parameters), longest first inside a preset (the 32 lanes of a
+         * warp then run a similar number of windows), and every preset group is padded to a whole CTA
+         * with VS_NO_CHUNK rows */
+        std::vector<uint32_t> &order = sl.plan_order;
+        order.clear();
+        sl.plan_groups.assign(n_slabs, {});
+        sl.plan_slab_r0.assign(n_slabs + 1, 0);
         for (size_t k = 0; k < n_slabs; k++) {
-            slab_r0[k] = order.size();
+            sl.plan_slab_r0[k] = order.size();
             std::vector<uint32_t> ids(slab_c0[k + 1] - slab_c0[k]);
             for (size_t c = 0; c < ids.size(); c++) ids[c] = (uint32_t)(slab_c0[k] + c);
             auto preset_of = [&](uint32_t c) -> int { return b.mode == VS_MODE_FLOW ? 0 : hs[s0 + hc[c].stream].preset; };
@@ -593,12 +636,29 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 const size_t r0 = order.size();
                 for (size_t i = i0; i < i1; i++) order.push_back(ids[i]);
                 while (order.size() % VS_NT) order.push_back(VS_NO_CHUNK);
-                slab_groups[k].push_back({r0, order.size(), pr});
+                sl.plan_groups[k].push_back({r0, order.size(), pr});
                 i0 = i1;
             }
         }
-        slab_r0[n_slabs] = order.size();
-        const size_t nrows = order.size();
+        sl.plan_slab_r0[n_slabs] = order.size();
+        sl.plan_sig.swap(sig);
+        prof.mark("row order");
+        }
+        const std::vector<VsChunk> &hc = sl.plan_chunks;
+        const std::vector<uint32_t> &order = sl.plan_order;
+        const std::vector<size_t> &slab_c0 = sl.plan_slab_c0, &slab_r0 = sl.plan_slab_r0;
+        const std::vector<std::vector<Slot::PlanGroup>> &slab_groups = sl.plan_groups;
+        typedef Slot::PlanGroup Group;
+        const uint64_t tab_total = sl.plan_tab_total, warm_total = sl.plan_warm_total;
+        {
+            uint32_t c0acc = 0;
+            uint64_t tacc = 0;
+            for (size_t i = s0; i < s1; i++) {
+                hs[i].chunk0 = c0acc; hs[i].n_chunks = sl.plan_nch[i - s0]; hs[i].tab_off = tacc;
+                c0acc += hs[i].n_chunks; tacc += hs[i].tab_cap;
+            }
+        }
+        const size_t nc = hc.size(), nrows = order.size();
         ctx->timing.chunks += (uint32_t)nc;
         ctx->timing.samples += total;
         ctx->timing.warmup_samples += warm_total;
@@ -662,7 +722,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             in_span_max = std::max(in_span_max, gm.in_max - gm.in_min);
         }
         if (!out_dev) {
-            for (int d = 0; d < (n_slabs > 1 ? 2 : 1); d++) {
+            for (int d = 0; d < 2; d++) {
                 if ((rc = dev_reserve(ctx, sl, sl.pcm[d], span_max * sizeof(int16_t) + 64))) return rc;
                 if (b.raw_out && (rc = dev_reserve(ctx, sl, sl.raw[d], span_max * sizeof(double) + 64))) return rc;
                 if (b.mode == VS_MODE_FILTER && (rc = dev_reserve(ctx, sl, sl.flowin[d], in_span_max * sizeof(int16_t) + 64))) return rc;
@@ -692,18 +752,19 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         ctx->timing.h2d_bytes += ns * sizeof(VsStream) + nc * sizeof(VsChunk) + nrows * sizeof(uint32_t);
         CU(cudaMemsetAsync(sl.status.p, 0, sizeof(int32_t), sl.compute));
 
+        prof.mark("reserve + descriptor upload");
         cudaEvent_t t_first = nullptr;
         if (g == 0) { t_first = timing_event(sl); CU(cudaEventRecord(t_first, sl.compute)); }
 
         for (size_t k = 0; k < n_slabs; k++) {
             const size_t a0 = s0 + k * slab_streams, a1 = std::min(s1, a0 + slab_streams);
             const size_t c0 = slab_c0[k], c1 = slab_c0[k + 1];
-            const int d = (int)(k & 1);
+            const int d = (int)((sl.scratch_parity + k) & 1);
             int16_t *d_pcm = out_dev ? b.pcm_out : (int16_t *)sl.pcm[d].p;
             double *d_raw = b.raw_out ? (out_dev ? b.raw_out : (double *)sl.raw[d].p) : nullptr;
             const int16_t *d_in = nullptr;
 
-            if (!out_dev && k >= 2) CU(cudaStreamWaitEvent(sl.compute, sl.slab_done[d], 0));
+            if (!out_dev && sl.slab_done_valid[d]) CU(cudaStreamWaitEvent(sl.compute, sl.slab_done[d], 0));   /* its last D2H */
 
             if (b.mode == VS_MODE_FILTER) {
                 if (out_dev) d_in = b.flow_in;
@@ -792,6 +853,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 }
                 CU(flush(run_lo, run_hi));
                 CU(cudaEventRecord(sl.slab_done[d], sl.copy));
+                sl.slab_done_valid[d] = true;
             }
         }
         if (want_log) ctx->timing.d2h_bytes += (log_hi - log_lo) * sizeof(vs_period_rec);
@@ -800,15 +862,19 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         if (want_log && b.log->count)
             CU(cudaMemcpyAsync(sl.h_nper.p, sl.nper.p, ns * sizeof(uint32_t), cudaMemcpyDeviceToHost, sl.compute));
         CU(cudaMemcpyAsync(sl.h_status.p, sl.status.p, sizeof(int32_t), cudaMemcpyDeviceToHost, sl.compute));
-        if (!out_dev) CU(cudaStreamWaitEvent(sl.compute, sl.slab_done[(n_slabs - 1) & 1], 0));
+        if (!out_dev) sl.scratch_parity = (unsigned)((sl.scratch_parity + n_slabs) & 1);
         if (g == 0) { cudaEvent_t t_last = timing_event(sl); CU(cudaEventRecord(t_last, sl.compute)); }
         CU(cudaEventRecord(sl.h2d_done, sl.compute));                 /* "call done" for this slot */
     }
 
+    prof.mark("launches enqueued");
     /* ---- 5. host buffers: the call returns when the data has landed -------------------------- */
-    if (!out_dev || want_log) {
+    const bool may_return_early = ctx->opt_async_host && out_kind == PK_HOST_PINNED && !want_log &&
+                                  (!b.raw_out || raw_kind == PK_HOST_PINNED) && (!b.flow_in || in_kind == PK_HOST_PINNED);
+    if ((!out_dev && !may_return_early) || want_log) {
         const int rc = vs_sync(ctx);
         if (rc) return rc;
+        prof.mark("sync (data landed)");
         if (want_log && b.log->count) {
             for (size_t g = 0; g < nslots; g++) {
                 const size_t s0 = cut[g], s1 = cut[g + 1];
@@ -942,6 +1008,7 @@ int vs_ctx_set_option(vs_ctx *ctx, int option, double value)
     case VS_OPT_SLAB_STREAMS: ctx->opt_slab = value > 0 ? (int)value : 0; return VS_OK;
     case VS_OPT_TARGET_WARPS: if (!(value > 0)) return VS_EINVAL; ctx->opt_warps = value; return VS_OK;
     case VS_OPT_LONG_SCAN: ctx->opt_long_scan = value != 0.0; return VS_OK;
+    case VS_OPT_ASYNC_HOST: ctx->opt_async_host = value != 0.0; return VS_OK;
     default: return VS_EINVAL;
     }
 }
