@@ -31,7 +31,6 @@
 #include "vs_internal.h"
 
 #define VS_RAND_MAX_D 2147483647.0
-#define VS_PB 4               /* pitch periods per batch of the plan kernel's fast path */
 
 /* Filter coefficients reach the DFMAs as constant-bank operands (kernel parameters, VsRenderArgs::ncf;
  * one launch per vowel preset).  On B200 a DFMA with two register operands + one constant operand
@@ -67,29 +66,6 @@ __device__ __forceinline__ double vs_div_const(double r, double d, double inv)
     const double rem = __fma_rn(-q0, d, r);
     return __fma_rn(rem, inv, q0);
 }
-/* n / d, branch-free: float-seeded Newton reciprocal, quotient + FMA residual correction, then an
- * exact check.  rem = n - q*d is computed exactly by the FMA when q is within an ulp of n/d, and q is
- * THE correctly rounded quotient iff |rem| < ulp(q)/2 * |d| (a quotient of doubles is never a tie).
- * When the check cannot confirm that (or anything was not finite) `doubt` is raised and the caller
- * redoes the work with __ddiv_rn; this keeps the common path free of control flow, so independent
- * divisions overlap (CUDA's own division has a conditional slow-path call in every instance). */
-__device__ __forceinline__ double vs_div_checked(double n, double d, bool &doubt)
-{
-    double y = (double)__frcp_rn((float)d);
-    y = __fma_rn(y, __fma_rn(-d, y, 1.0), y);
-    y = __fma_rn(y, __fma_rn(-d, y, 1.0), y);
-    y = __fma_rn(y, __fma_rn(-d, y, 1.0), y);
-    const double q0 = __dmul_rn(n, y);
-    const double q = __fma_rn(__fma_rn(-q0, d, n), y, q0);
-    const double rem = __fma_rn(-q, d, n);
-    /* ulp(q)/2 = 2^(e-53) for a normal q with unbiased exponent e */
-    const int e = (__double2hiint(q) >> 20) & 0x7ff;
-    const double half_ulp = __hiloint2double((e - 53) << 20, 0);
-    const bool sure = (e > 60 && e < 0x7fe) && (fabs(rem) < __dmul_rn(half_ulp, fabs(d)));
-    doubt = doubt || (!sure && !(q == 0.0 && rem == 0.0));
-    return q;
-}
-
 #define VS_INV_RM  (1.0 / 2147483647.0)
 #define VS_RM4     (2147483647.0 * 10000.0)
 #define VS_INV_RM4 (1.0 / (2147483647.0 * 10000.0))
@@ -110,14 +86,6 @@ __device__ __forceinline__ int32_t vs_rng_next(VsRng &g)
     g.r[g.f * VS_NT] = v;
     g.f = (g.f == VS_RNG_DEG - 1) ? 0 : g.f + 1;
     return (int32_t)(v >> 1);
-}
-
-/* undo the last vs_rng_next(): the additive generator is invertible */
-__device__ __forceinline__ void vs_rng_prev(VsRng &g)
-{
-    g.f = (g.f == 0) ? VS_RNG_DEG - 1 : g.f - 1;
-    const int b = g.f >= 3 ? g.f - 3 : g.f + 28;
-    g.r[g.f * VS_NT] -= g.r[b * VS_NT];
 }
 
 __device__ void vs_rng_seed(VsRng &g, uint32_t seed)
@@ -178,21 +146,12 @@ __device__ __forceinline__ int vs_add_clip(int x, int w)
 /* ================================================================================================
  * PLAN: one thread per stream
  * ============================================================================================== */
-/* one pitch period, sequentially: the reference's loop body (flowgen_shimmer.c:246-423), draw by draw */
-struct VsPlanState {
-    int T, T4, ndw;
-    float dper, dsh;
-    uint32_t count, np, next_c, next_target;
-    int guard;
-};
-
 template <bool LOG>
 __global__ void __launch_bounds__(VS_NT) vs_plan_kernel(const VsPlanArgs a)
 {
     __shared__ uint32_t s_rng[VS_RNG_DEG * VS_NT];
-    const uint32_t s_raw = blockIdx.x * VS_NT + threadIdx.x;
-    const bool valid = s_raw < a.n_streams;
-    const uint32_t s = valid ? s_raw : 0u;         /* surplus lanes shadow stream 0 but never write */
+    const uint32_t s = blockIdx.x * VS_NT + threadIdx.x;
+    if (s >= a.n_streams) return;
     const VsStream st = a.streams[s];
     VsRng g;
     g.r = s_rng + threadIdx.x;
@@ -202,7 +161,6 @@ __global__ void __launch_bounds__(VS_NT) vs_plan_kernel(const VsPlanArgs a)
     const bool do_shm = (st.flags & VS_F_SHIMMER) && st.shimmer != 0.0f;  /* :295 */
     const bool noise = (st.flags & VS_F_NOISE) != 0;                      /* :373 */
     const bool pulse = LOG || noise;
-    const bool fast = !LOG && !noise;
     const int P = st.P, T2 = st.T2;
     const float Pf = (float)P, ampf = (float)st.amp;
     const float t_hi = __fmul_rn(1.2f, Pf), t_lo = __fmul_rn(0.8f, Pf);
@@ -215,7 +173,6 @@ __global__ void __launch_bounds__(VS_NT) vs_plan_kernel(const VsPlanArgs a)
     const double *ct = ht + T2;
     const int DCi = (int)ceilf(st.DC);             /* (float)x < DC  <=>  x < ceil(DC) for integer x */
     const int DCs = st.DCs;
-    const uint32_t npert_fixed = (do_jit ? 1u : 0u) + (do_shm ? 1u : 0u) + 1u;
 
     int T = P, T4 = 0, ndw = 0;
     float dper = 0.0f, dsh = 0.0f;
@@ -225,104 +182,12 @@ __global__ void __launch_bounds__(VS_NT) vs_plan_kernel(const VsPlanArgs a)
     uint32_t next_target = st.n_chunks ? chunks[0].gen_target : 0xffffffffu;
     vs_period_rec *log = LOG ? (vs_period_rec *)a.log + st.log_off : nullptr;
     int guard = 0;
-    bool live = valid;                              /* this lane still has periods to produce */
 
-#define VS_PLAN_FAIL(code) do { atomicExch(a.status, (code)); live = false; } while (0)
-
-    /* The loop is warp-synchronous: every iteration all lanes first try a batch on the fast path,
-     * reconverge, then the lanes that need it run sequential periods, and reconverge again.  (Lanes
-     * that leave a data-dependent loop early would otherwise never rejoin the rest of the warp.) */
-    while (__any_sync(VS_FULL, live)) {
-        bool need_seq = live && !fast;
-
-        /* ---- fast path (no noise, no log): VS_PB periods per step ---------------------------------
-         * Without noise a period consumes a fixed number of draws unless a rejection loop re-draws, so
-         * the draws of the next VS_PB periods and everything that depends only on them (J, S, Knew,
-         * the state-independent quotient 2*P*J/(2-J), ...) are computed up front with VS_PB-way
-         * instruction-level parallelism; only the two short random-walk recurrences stay serial.
-         * Same operations in the same order as the sequential path, hence the same bits.  A rejected
-         * candidate rewinds the (invertible) generator to the start of that period, which is then
-         * replayed sequentially. */
-        if (live && fast) {
-            int32_t rj[VS_PB], rs[VS_PB], rkk[VS_PB];
-#pragma unroll
-            for (int k = 0; k < VS_PB; k++) {
-                rj[k] = do_jit ? vs_rng_next(g) : 0;
-                rs[k] = do_shm ? vs_rng_next(g) : 0;
-                rkk[k] = vs_rng_next(g);
-            }
-            double ja[VS_PB], jd[VS_PB], jq[VS_PB], sa[VS_PB], sd[VS_PB], sq[VS_PB];
-            float kn[VS_PB];
-            bool doubt = false;                               /* a precomputed quotient could not be confirmed */
-#pragma unroll
-            for (int k = 0; k < VS_PB; k++) {
-                double t = vs_div_const((double)rj[k], VS_RM4, VS_INV_RM4);
-                t = __dmul_rn(__dmul_rn(t, 40000.0), jit);
-                const double J = (double)__double2float_rn(__dsub_rn(t, jit2));
-                jd[k] = __dsub_rn(2.0, J);
-                ja[k] = __dadd_rn(2.0, J);
-                jq[k] = vs_div_checked(__dmul_rn(P2, J), jd[k], doubt);
-                const float eps = __fmul_rn((float)rs[k], 4.656612873077393e-10f);
-                const double S = (double)__double2float_rn(__dsub_rn(__dmul_rn(__dmul_rn((double)eps, 4.0), shm), shm2));
-                sd[k] = __dsub_rn(2.0, S);
-                sa[k] = __dadd_rn(2.0, S);
-                sq[k] = vs_div_checked(__dmul_rn(amp2, S), sd[k], doubt);
-                const double kq = __dsub_rn(vs_div_const((double)rkk[k], VS_RAND_MAX_D, VS_INV_RM), 0.5);
-                kn[k] = __double2float_rn(__dmul_rn(Kbase, __dadd_rn(1.0, __dmul_rn(kv2, kq))));
-            }
-            int stop = doubt ? 0 : -1;                        /* first period of the batch that was NOT committed */
-            if (doubt) need_seq = true;
-#pragma unroll
-            for (int k = 0; k < VS_PB; k++) {
-                if (stop < 0) {
-                    float curj = dper, curs = dsh, A = ampf;
-                    int Tn = T;
-                    bool ok = true, doubt2 = false;
-                    if (do_jit) {
-                        curj = __double2float_rn(__dadd_rn(vs_div_checked(__dmul_rn((double)dper, ja[k]), jd[k], doubt2), jq[k]));
-                        Tn = (int)vs_d2s(ceil((double)__fadd_rn(Pf, curj)));
-                        ok = !((float)Tn > t_hi || (float)Tn < t_lo);
-                    }
-                    if (do_shm) {
-                        curs = __double2float_rn(__dadd_rn(vs_div_checked(__dmul_rn((double)dsh, sa[k]), sd[k], doubt2), sq[k]));
-                        A = __fadd_rn(ampf, curs);
-                        ok = ok && !(A > a_hi || A < a_lo);
-                    }
-                    if (!ok || doubt2 || Tn < 1 || Tn > 32767) { stop = k; need_seq = true; }
-                    else if (np >= st.tab_cap) { VS_PLAN_FAIL(VS_ENOMEM); stop = k; }
-                    else {
-                        dper = curj; dsh = curs; T = Tn;
-                        while (next_target < count + (uint32_t)T) {
-                            chunks[next_c].first_period = np;
-                            next_c++;
-                            next_target = next_c < st.n_chunks ? chunks[next_c].gen_target : 0xffffffffu;
-                        }
-                        VsPeriod e;
-                        e.Ad = (double)A; e.Kd = (double)kn[k]; e.start = count;
-                        e.T_np = (uint32_t)T | (npert_fixed << 16);
-                        e.T34 = (uint32_t)(2 * T2);
-                        e.ndw = 0;
-                        tab[np] = e;
-                        count += (uint32_t)T;
-                        np++;
-                        if (count >= st.n) { live = false; stop = k + 1; }
-                    }
-                }
-            }
-            /* rewind to the first draw of the first uncommitted period */
-            if (need_seq)
-                for (uint32_t k = 0; k < (uint32_t)(VS_PB - stop) * npert_fixed; k++) vs_rng_prev(g);
-        }
-        __syncwarp();
-
-        /* ---- sequential periods: noise / log streams always, fast streams after a rejection --------- */
-        for (int rep = 0; rep < (fast ? 1 : VS_PB); rep++) {
-        if (need_seq && live) {
+    do {
         uint32_t nd = 0;
         if (do_jit) {                                                     /* :276-290 */
             const double prev = (double)dper;
             float cur;
-            bool bad;
             do {
                 const int32_t r = vs_rng_next(g); nd++;
                 double t = vs_div_const((double)r, VS_RM4, VS_INV_RM4);
@@ -333,16 +198,14 @@ __global__ void __launch_bounds__(VS_NT) vs_plan_kernel(const VsPlanArgs a)
                 const double q2 = __ddiv_rn(__dmul_rn(P2, J), den);
                 cur = __double2float_rn(__dadd_rn(q1, q2));
                 T = (int)vs_d2s(ceil((double)__fadd_rn(Pf, cur)));
-                bad = (float)T > t_hi || (float)T < t_lo;
-                if (bad && ++guard > (1 << 22)) { VS_PLAN_FAIL(VS_ERANGE); break; }
-            } while (bad);
+                if (++guard > (1 << 22)) { atomicExch(a.status, VS_ERANGE); return; }
+            } while ((float)T > t_hi || (float)T < t_lo);
             dper = cur;
         }
         float A = ampf, S = 0.0f;
-        if (do_shm && live) {                                             /* :296-306 */
+        if (do_shm) {                                                     /* :296-306 */
             const double prev = (double)dsh;
             float cur;
-            bool bad;
             do {
                 const int32_t r = vs_rng_next(g); nd++;
                 const float eps = __fmul_rn((float)r, 4.656612873077393e-10f);   /* / (float)RAND_MAX == * 2^-31, exact */
@@ -352,13 +215,12 @@ __global__ void __launch_bounds__(VS_NT) vs_plan_kernel(const VsPlanArgs a)
                 const double q2 = __ddiv_rn(__dmul_rn(amp2, (double)S), den);
                 cur = __double2float_rn(__dadd_rn(q1, q2));
                 A = __fadd_rn(ampf, cur);
-                bad = A > a_hi || A < a_lo;
-                if (bad && ++guard > (1 << 22)) { VS_PLAN_FAIL(VS_ERANGE); break; }
-            } while (bad);
+                if (++guard > (1 << 22)) { atomicExch(a.status, VS_ERANGE); return; }
+            } while (A > a_hi || A < a_lo);
             dsh = cur;
         }
-        if (live && (T < 1 || T > 32767)) VS_PLAN_FAIL(VS_ERANGE);
-        if (live) {
+        if (T < 1 || T > 32767) { atomicExch(a.status, VS_ERANGE); return; }
+
         /* closure-speed draw, always consumed (:325) */
         const int32_t rk = vs_rng_next(g); nd++;
         const double kq = __dsub_rn(vs_div_const((double)rk, VS_RAND_MAX_D, VS_INV_RM), 0.5);
@@ -419,32 +281,26 @@ __global__ void __launch_bounds__(VS_NT) vs_plan_kernel(const VsPlanArgs a)
         }
 
         if (np >= st.tab_cap || nd > 65535u || T3 > 65535 || T4 > 65535) {
-            VS_PLAN_FAIL(np >= st.tab_cap ? VS_ENOMEM : VS_ERANGE);
-        } else {
-            VsPeriod e;
-            e.Ad = (double)A; e.Kd = (double)Knew; e.start = count;
-            e.T_np = (uint32_t)T | (nd << 16);
-            e.T34 = (uint32_t)T3 | ((uint32_t)T4 << 16);
-            e.ndw = ndw;
-            tab[np] = e;
-            if (LOG) {
-                vs_period_rec r;
-                r.T = T; r.T2 = T2; r.T3 = T3; r.T4 = T4; r.A = A; r.Knew = Knew; r.S = S;
-                r.ndraws = (int32_t)(nd + n_noise); r.ndw = ndw; r.x_pow = x_pow; r.w_pow = w_pow; r.reserved = 0;
-                r.start = count;
-                log[np] = r;
-            }
-            count += (uint32_t)T;                                             /* :413 */
-            np++;
-            if (count >= st.n) live = false;                                  /* :423 */
+            atomicExch(a.status, np >= st.tab_cap ? VS_ENOMEM : VS_ERANGE);
+            return;
         }
+        VsPeriod e;
+        e.Ad = (double)A; e.Kd = (double)Knew; e.start = count;
+        e.T_np = (uint32_t)T | (nd << 16);
+        e.T34 = (uint32_t)T3 | ((uint32_t)T4 << 16);
+        e.ndw = ndw;
+        tab[np] = e;
+        if (LOG) {
+            vs_period_rec r;
+            r.T = T; r.T2 = T2; r.T3 = T3; r.T4 = T4; r.A = A; r.Knew = Knew; r.S = S;
+            r.ndraws = (int32_t)(nd + n_noise); r.ndw = ndw; r.x_pow = x_pow; r.w_pow = w_pow; r.reserved = 0;
+            r.start = count;
+            log[np] = r;
         }
-        }
-        }
-        __syncwarp();
-    }
-#undef VS_PLAN_FAIL
-    if (valid) a.n_periods[s] = np;
+        count += (uint32_t)T;                                             /* :413 */
+        np++;
+    } while (count < st.n);                                               /* :423 */
+    a.n_periods[s] = np;
 }
 
 /* ================================================================================================
