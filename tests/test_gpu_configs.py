@@ -1,0 +1,131 @@
+"""BASELINE.json's configurations at (or near) full size on the GPU: spot-checked against the oracle on a
+seeded sample of streams, plus size-independent properties (idempotence, shard invariance, chunking
+invariance of the flow, exact stream lengths)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vs():
+    from voice_synth_b200 import api
+    return api
+
+
+@pytest.fixture(scope="module")
+def ctx(vs):
+    c = vs.Context()
+    yield c
+    c.close()
+
+
+def _opar(oracle, vs, p, i):
+    q = oracle.FlowPar()
+    for k in ("dur", "jitter", "cq", "K", "F0", "DC", "noise", "Kvar", "shimmer"):
+        setattr(q, k, float(getattr(p, k)[i]))
+    q.fs, q.amp, q.seed = int(p.fs[i]), int(p.amp[i]), int(p.seed[i])
+    q.has_jitter, q.has_shimmer, q.has_noise = [int(bool(p.flags[i] & b)) for b in (1, 2, 4)]
+    return q
+
+
+def _check_sample(oracle, vs, p, f, pcm, offs, ns, idx, flow=None, foffs=None):
+    worst = 0
+    for i in idx:
+        oflow = oracle.flowgen(_opar(oracle, vs, p, i))
+        if flow is not None:
+            assert np.array_equal(flow[int(foffs[i]): int(foffs[i]) + int(ns[i])], oflow), f"flow of stream {i}"
+        want = oracle.vowel(oflow, chr(f.preset[i]), gain=float(f.gain[i]), pre=float(f.pre[i]))
+        got = pcm[int(offs[i]): int(offs[i]) + int(ns[i])]
+        d = int(np.abs(got.astype(np.int32) - want.astype(np.int32)).max())
+        worst = max(worst, d)
+        assert d <= 1, f"stream {i}: {d} LSB"
+    return worst
+
+
+def test_cfg2_full_batch(ctx, vs, oracle):
+    """4096 streams x 1 s, every preset, fused kernel, auto chunking (the bench workload)"""
+    from voice_synth_b200 import workloads
+    p, f = workloads.cfg2()
+    pcm, offs, ns = ctx.synth_batch(p, f)
+    t = ctx.timing()
+    assert t["samples"] == 4096 * 22050 and t["chunks"] > 4096
+    flow, foffs, _ = ctx.flowgen_batch(p)
+    rng = np.random.default_rng(2)
+    idx = sorted(set(rng.integers(0, p.n, 40).tolist()) | {0, 1, 4095})
+    _check_sample(oracle, vs, p, f, pcm, offs, ns, idx, flow, foffs)
+    # idempotence: the same call again gives the same bytes
+    pcm2, _, _ = ctx.synth_batch(p, f)
+    assert np.array_equal(pcm, pcm2)
+    # shard invariance: synthesising a sub-range alone gives the same rows (what a multi-GPU split does)
+    sub = np.arange(1000, 1512)
+    spcm, soffs, sns = ctx.synth_batch(p.select(sub), f.select(sub))
+    for k, i in enumerate(sub[::37]):
+        kk = int(k * 37)
+        a = spcm[int(soffs[kk]): int(soffs[kk]) + int(sns[kk])]
+        b = pcm[int(offs[i]): int(offs[i]) + int(ns[i])]
+        assert np.abs(a.astype(np.int32) - b.astype(np.int32)).max() <= 1      # chunk boundaries differ -> +-1 LSB allowed
+    # flow is bit-exact regardless of how the batch is cut
+    sflow, sfo, _ = ctx.flowgen_batch(p.select(sub))
+    for k, i in enumerate(sub[::37]):
+        kk = int(k * 37)
+        assert np.array_equal(sflow[int(sfo[kk]): int(sfo[kk]) + int(sns[kk])], flow[int(foffs[i]): int(foffs[i]) + int(ns[i])])
+
+
+def test_cfg3_noise_grid_shard(ctx, vs, oracle):
+    """one GPU's shard of the jitter x shimmer x F0 grid: 8192 streams x 2 s with glottal noise"""
+    from voice_synth_b200 import workloads
+    p, f = workloads.cfg3(n=8192, first=3 * 8192)
+    pcm, offs, ns = ctx.synth_batch(p, f)
+    assert int(ns.sum()) == 8192 * 44100
+    flow, foffs, _ = ctx.flowgen_batch(p)
+    rng = np.random.default_rng(3)
+    idx = sorted(set(rng.integers(0, p.n, 24).tolist()) | {0, 8191})
+    _check_sample(oracle, vs, p, f, pcm, offs, ns, idx, flow, foffs)
+
+
+def test_cfg4_ten_minute_stream(ctx, vs, oracle):
+    """single 600 s stream, vowel /i/: 13 230 000 samples through the time-chunked filter"""
+    from voice_synth_b200 import workloads
+    p, f = workloads.cfg4()
+    flow, _, ns = ctx.flowgen_batch(p)
+    assert int(ns[0]) == 13230000
+    oflow = oracle.flowgen(_opar(oracle, vs, p, 0))
+    assert np.array_equal(flow, oflow)
+    pcm, _, _ = ctx.synth_batch(p, f)
+    assert ctx.timing()["chunks"] > 100
+    want = oracle.vowel(oflow, "i")
+    d = np.abs(pcm.astype(np.int32) - want.astype(np.int32))
+    assert int(d.max()) <= 1
+    print("cfg4: samples differing by 1 LSB:", int((d > 0).sum()), "of", d.size)
+    # the stand-alone filter on the reference-exact flow gives the same
+    out, _ = ctx.vowel_filter_batch(oflow, [oflow.size], f)
+    assert int(np.abs(out.astype(np.int32) - want.astype(np.int32)).max()) <= 1
+
+
+def test_cfg5_corpus_slice(ctx, vs, oracle):
+    """a slice of the 1M-utterance sweep: mixed noise / no-noise streams, hashed parameters"""
+    from voice_synth_b200 import workloads
+    p, f = workloads.cfg5(n=16384, first=500000)
+    pcm, offs, ns = ctx.synth_batch(p, f)
+    rng = np.random.default_rng(5)
+    idx = sorted(set(rng.integers(0, p.n, 24).tolist()))
+    _check_sample(oracle, vs, p, f, pcm, offs, ns, idx)
+
+
+def test_edge_shapes(ctx, vs, oracle):
+    """ragged batch: shortest legal stream, very high and very low F0, a stream shorter than one window"""
+    args = ["-d 0.5 -f 50 -g 60", "-d 0.5 -f 1000 -g 1100 -j 1 -s 1", "-d 0.5 -r 100 -f 50 -g 60 -s 2",
+            "-d 0.5 -r 8000 -f 399 -g 400 -j 3 -n 15", "-d 1.25 -f 120 -c 0 -s 3", "-d 0.75 -f 120 -a 0 -j 1"]
+    p = vs.FlowParams.from_cli(args, [9, 8, 7, 6, 5, 4])
+    f = vs.FilterParams(p.n, "aiu123")
+    flow, foffs, ns = ctx.flowgen_batch(p)
+    pcm, offs, _ = ctx.synth_batch(p, f)
+    _check_sample(oracle, vs, p, f, pcm, offs, ns, range(p.n), flow, foffs)
+    assert int(ns[2]) == 50                                   # 0.5 s at 100 Hz: less than one render window
+    # n == 0 streams are rejected, not silently skipped
+    bad = vs.FlowParams(1, dur=0.0)
+    with pytest.raises(vs.VsError):
+        ctx.flowgen_batch(bad)
+    with pytest.raises(vs.VsError):
+        ctx.synth_batch(vs.FlowParams(1), vs.FilterParams(1, "x"))
