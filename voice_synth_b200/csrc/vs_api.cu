@@ -49,13 +49,16 @@ struct Slot {
     cudaStream_t compute = nullptr;
     bool own_compute = true;
     cudaStream_t copy = nullptr;
-    cudaEvent_t h2d_done = nullptr;
+    cudaStream_t plan = nullptr;                     /* descriptor upload + plan kernel of call k+1 overlap render(k) */
+    cudaEvent_t call_done[2] = {nullptr, nullptr};   /* everything of the call that used parity p has finished (compute) */
+    cudaEvent_t plan_done[2] = {nullptr, nullptr};
+    unsigned call_parity = 0;
     cudaEvent_t slab_done[2] = {nullptr, nullptr};   /* D2H of the slab using pcm[k] finished */
     cudaEvent_t slab_ready = nullptr;                /* render of the current slab finished   */
     cudaStream_t pstream[VS_NUM_PRESETS] = {};       /* one side stream per vowel preset: the per-preset   */
     cudaEvent_t pfork = nullptr, pjoin[VS_NUM_PRESETS] = {};   /* render launches of a slab run concurrently */
-    DevBuf streams, chunks, order, table, snap, nper, costab, coef, status, pcm[2], raw[2], flowin[2], log;
-    PinBuf h_streams, h_chunks, h_order, h_nper, h_status;
+    DevBuf streams[2], chunks[2], order[2], table[2], snap[2], nper[2], status[2], costab, coef, pcm[2], raw[2], flowin[2], log;
+    PinBuf h_streams[2], h_chunks[2], h_order[2], h_nper[2], h_status[2];
     size_t costab_uploaded = 0;
     std::vector<cudaEvent_t> tev;                    /* timing events (slot 0 only) */
     size_t tev_used = 0;
@@ -117,6 +120,7 @@ int dev_reserve(vs_ctx *ctx, Slot &s, DevBuf &b, size_t bytes)
 {
     if (bytes <= b.cap) return VS_OK;
     if (b.p) {
+        CU(cudaStreamSynchronize(s.plan));
         CU(cudaStreamSynchronize(s.compute));
         CU(cudaStreamSynchronize(s.copy));
         CU(cudaFree(b.p));
@@ -663,16 +667,20 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         ctx->timing.samples += total;
         ctx->timing.warmup_samples += warm_total;
 
-        /* device memory */
+        /* device memory: descriptor/table buffers alternate between calls (parity cp), so that the
+         * upload + plan kernel of this call can run while the previous call still renders */
+        const unsigned cp = sl.call_parity;
+        sl.call_parity ^= 1u;
+        CU(cudaEventSynchronize(sl.call_done[cp]));                   /* the call before the previous one is done with them */
         int rc;
-        if ((rc = dev_reserve(ctx, sl, sl.streams, ns * sizeof(VsStream)))) return rc;
-        if ((rc = dev_reserve(ctx, sl, sl.chunks, nc * sizeof(VsChunk)))) return rc;
-        if ((rc = dev_reserve(ctx, sl, sl.order, nrows * sizeof(uint32_t) + 16))) return rc;
-        if ((rc = dev_reserve(ctx, sl, sl.nper, ns * sizeof(uint32_t)))) return rc;
-        if ((rc = dev_reserve(ctx, sl, sl.status, sizeof(int32_t)))) return rc;
+        if ((rc = dev_reserve(ctx, sl, sl.streams[cp], ns * sizeof(VsStream)))) return rc;
+        if ((rc = dev_reserve(ctx, sl, sl.chunks[cp], nc * sizeof(VsChunk)))) return rc;
+        if ((rc = dev_reserve(ctx, sl, sl.order[cp], nrows * sizeof(uint32_t) + 16))) return rc;
+        if ((rc = dev_reserve(ctx, sl, sl.nper[cp], ns * sizeof(uint32_t)))) return rc;
+        if ((rc = dev_reserve(ctx, sl, sl.status[cp], sizeof(int32_t)))) return rc;
         if (b.mode != VS_MODE_FILTER) {
-            if ((rc = dev_reserve(ctx, sl, sl.table, (tab_total + 8) * sizeof(VsPeriod)))) return rc;
-            if (any_noise && (rc = dev_reserve(ctx, sl, sl.snap, nc * 32 * sizeof(uint32_t)))) return rc;
+            if ((rc = dev_reserve(ctx, sl, sl.table[cp], (tab_total + 8) * sizeof(VsPeriod)))) return rc;
+            if (any_noise && (rc = dev_reserve(ctx, sl, sl.snap[cp], nc * 32 * sizeof(uint32_t)))) return rc;
             if ((rc = dev_reserve(ctx, sl, sl.costab, std::max<size_t>(8, ctx->cos_host.size() * sizeof(double))))) return rc;
             if (sl.costab_uploaded != ctx->cos_host.size()) {
                 /* tables only ever grow; a synchronous copy keeps the host vector free to grow again */
@@ -682,11 +690,11 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 sl.costab_uploaded = ctx->cos_host.size();
             }
         }
-        if ((rc = pin_reserve(ctx, sl.h_streams, ns * sizeof(VsStream)))) return rc;
-        if ((rc = pin_reserve(ctx, sl.h_chunks, nc * sizeof(VsChunk)))) return rc;
-        if ((rc = pin_reserve(ctx, sl.h_order, nrows * sizeof(uint32_t) + 16))) return rc;
-        if ((rc = pin_reserve(ctx, sl.h_nper, ns * sizeof(uint32_t)))) return rc;
-        if ((rc = pin_reserve(ctx, sl.h_status, sizeof(int32_t)))) return rc;
+        if ((rc = pin_reserve(ctx, sl.h_streams[cp], ns * sizeof(VsStream)))) return rc;
+        if ((rc = pin_reserve(ctx, sl.h_chunks[cp], nc * sizeof(VsChunk)))) return rc;
+        if ((rc = pin_reserve(ctx, sl.h_order[cp], nrows * sizeof(uint32_t) + 16))) return rc;
+        if ((rc = pin_reserve(ctx, sl.h_nper[cp], ns * sizeof(uint32_t)))) return rc;
+        if ((rc = pin_reserve(ctx, sl.h_status[cp], sizeof(int32_t)))) return rc;
 
         /* log span of this slot */
         uint64_t log_lo = 0, log_hi = 0;
@@ -699,7 +707,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 hs[i].log_off = b.log->rec_offsets[i] - log_lo;
             }
             if ((rc = dev_reserve(ctx, sl, sl.log, std::max<uint64_t>(1, log_hi - log_lo) * sizeof(vs_period_rec)))) return rc;
-            CU(cudaMemsetAsync(sl.log.p, 0, (log_hi - log_lo) * sizeof(vs_period_rec), sl.compute));
+            CU(cudaMemsetAsync(sl.log.p, 0, (log_hi - log_lo) * sizeof(vs_period_rec), sl.plan));
         }
 
         /* device-side offsets: rows of a slab live at (offset - slab_min) + pad to keep the phase */
@@ -731,8 +739,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
 
         /* upload descriptors; the previous call on this slot must be done with the staging buffers
          * (everything above overlapped with it) */
-        CU(cudaEventSynchronize(sl.h2d_done));
-        VsStream *ps = (VsStream *)sl.h_streams.p;
+        VsStream *ps = (VsStream *)sl.h_streams[cp].p;
         for (size_t k = 0; k < n_slabs; k++) {
             const size_t a0 = s0 + k * slab_streams, a1 = std::min(s1, a0 + slab_streams);
             for (size_t i = a0; i < a1; i++) {
@@ -743,19 +750,42 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 }
             }
         }
-        memcpy(sl.h_chunks.p, hc.data(), nc * sizeof(VsChunk));
-        memcpy(sl.h_order.p, order.data(), nrows * sizeof(uint32_t));
-        *(int32_t *)sl.h_status.p = 0;
-        CU(cudaMemcpyAsync(sl.streams.p, sl.h_streams.p, ns * sizeof(VsStream), cudaMemcpyHostToDevice, sl.compute));
-        CU(cudaMemcpyAsync(sl.chunks.p, sl.h_chunks.p, nc * sizeof(VsChunk), cudaMemcpyHostToDevice, sl.compute));
-        CU(cudaMemcpyAsync(sl.order.p, sl.h_order.p, nrows * sizeof(uint32_t), cudaMemcpyHostToDevice, sl.compute));
+        memcpy(sl.h_chunks[cp].p, hc.data(), nc * sizeof(VsChunk));
+        memcpy(sl.h_order[cp].p, order.data(), nrows * sizeof(uint32_t));
+        *(int32_t *)sl.h_status[cp].p = 0;
+        CU(cudaMemcpyAsync(sl.streams[cp].p, sl.h_streams[cp].p, ns * sizeof(VsStream), cudaMemcpyHostToDevice, sl.plan));
+        CU(cudaMemcpyAsync(sl.chunks[cp].p, sl.h_chunks[cp].p, nc * sizeof(VsChunk), cudaMemcpyHostToDevice, sl.plan));
+        CU(cudaMemcpyAsync(sl.order[cp].p, sl.h_order[cp].p, nrows * sizeof(uint32_t), cudaMemcpyHostToDevice, sl.plan));
         ctx->timing.h2d_bytes += ns * sizeof(VsStream) + nc * sizeof(VsChunk) + nrows * sizeof(uint32_t);
-        CU(cudaMemsetAsync(sl.status.p, 0, sizeof(int32_t), sl.compute));
+        CU(cudaMemsetAsync(sl.status[cp].p, 0, sizeof(int32_t), sl.plan));
 
         prof.mark("reserve + descriptor upload");
-        cudaEvent_t t_first = nullptr;
-        if (g == 0) { t_first = timing_event(sl); CU(cudaEventRecord(t_first, sl.compute)); }
+        /* ---- plan stream: descriptors are up (above), now the plan kernel(s) of every slab -------- */
+        if (g == 0) { cudaEvent_t t_first = timing_event(sl); CU(cudaEventRecord(t_first, sl.plan)); }
+        if (b.mode != VS_MODE_FILTER) {
+            for (size_t k = 0; k < n_slabs; k++) {
+                const size_t a0 = s0 + k * slab_streams, a1 = std::min(s1, a0 + slab_streams);
+                VsPlanArgs pa;
+                memset(&pa, 0, sizeof pa);
+                pa.streams = (const VsStream *)sl.streams[cp].p + (a0 - s0);
+                pa.n_streams = (uint32_t)(a1 - a0);
+                pa.chunks = (VsChunk *)sl.chunks[cp].p;
+                pa.table = (VsPeriod *)sl.table[cp].p;
+                pa.rng_snap = any_noise ? (uint32_t *)sl.snap[cp].p : nullptr;
+                pa.n_periods = (uint32_t *)sl.nper[cp].p + (a0 - s0);
+                pa.costab = (const double *)sl.costab.p;
+                pa.log = want_log ? sl.log.p : nullptr;
+                pa.status = (int32_t *)sl.status[cp].p;
+                pa.need_pulse = want_log;
+                CU(vs_launch_plan(pa, want_log, sl.plan));
+                ctx->timing.launches++;
+            }
+        }
+        if (g == 0) { cudaEvent_t t_plan = timing_event(sl); CU(cudaEventRecord(t_plan, sl.plan)); }
+        CU(cudaEventRecord(sl.plan_done[cp], sl.plan));
+        CU(cudaStreamWaitEvent(sl.compute, sl.plan_done[cp], 0));
 
+        /* ---- compute stream: render (and copy) slab by slab ------------------------------------------ */
         for (size_t k = 0; k < n_slabs; k++) {
             const size_t a0 = s0 + k * slab_streams, a1 = std::min(s1, a0 + slab_streams);
             const size_t c0 = slab_c0[k], c1 = slab_c0[k + 1];
@@ -775,35 +805,15 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                     ctx->timing.h2d_bytes += (geom[k].in_max - geom[k].in_min) * sizeof(int16_t);
                 }
             }
-
-            cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
-            if (g == 0) { e0 = timing_event(sl); e1 = timing_event(sl); e2 = timing_event(sl); CU(cudaEventRecord(e0, sl.compute)); }
-
-            if (b.mode != VS_MODE_FILTER) {
-                VsPlanArgs pa;
-                memset(&pa, 0, sizeof pa);
-                pa.streams = (const VsStream *)sl.streams.p + (a0 - s0);
-                pa.n_streams = (uint32_t)(a1 - a0);
-                pa.chunks = (VsChunk *)sl.chunks.p;
-                pa.table = (VsPeriod *)sl.table.p;
-                pa.rng_snap = any_noise ? (uint32_t *)sl.snap.p : nullptr;
-                pa.n_periods = (uint32_t *)sl.nper.p + (a0 - s0);
-                pa.costab = (const double *)sl.costab.p;
-                pa.log = want_log ? sl.log.p : nullptr;
-                pa.status = (int32_t *)sl.status.p;
-                pa.need_pulse = want_log;
-                CU(vs_launch_plan(pa, want_log, sl.compute));
-                ctx->timing.launches++;
-            }
-            if (g == 0) CU(cudaEventRecord(e1, sl.compute));
+            if (g == 0) { cudaEvent_t e1 = timing_event(sl); CU(cudaEventRecord(e1, sl.compute)); }
 
             VsRenderArgs ra;
             memset(&ra, 0, sizeof ra);
-            ra.streams = (const VsStream *)sl.streams.p;
-            ra.chunks = (const VsChunk *)sl.chunks.p;
+            ra.streams = (const VsStream *)sl.streams[cp].p;
+            ra.chunks = (const VsChunk *)sl.chunks[cp].p;
             ra.n_chunks = (uint32_t)(c1 - c0);
-            ra.table = (const VsPeriod *)sl.table.p;
-            ra.rng_snap = any_noise ? (const uint32_t *)sl.snap.p : nullptr;
+            ra.table = (const VsPeriod *)sl.table[cp].p;
+            ra.rng_snap = any_noise ? (const uint32_t *)sl.snap[cp].p : nullptr;
             ra.costab = (const double *)sl.costab.p;
             ra.coef = (const double *)sl.coef.p;
             ra.flow_in = d_in;
@@ -817,7 +827,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             if (fork) CU(cudaEventRecord(sl.pfork, sl.compute));
             for (size_t gi = 0; gi < groups.size(); gi++) {
                 const Group &gr = groups[gi];
-                ra.order = (const uint32_t *)sl.order.p + gr.r0;
+                ra.order = (const uint32_t *)sl.order[cp].p + gr.r0;
                 ra.n_rows = (uint32_t)(gr.r1 - gr.r0);
                 for (int j = 0; j < VS_RING; j++) ra.ncf[j] = j <= VS_ORDER ? -vs_preset_den[gr.preset][j] : 0.0;
                 cudaStream_t st = fork ? sl.pstream[gi % VS_NUM_PRESETS] : sl.compute;
@@ -830,7 +840,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                     CU(cudaEventRecord(sl.pjoin[gi], sl.pstream[gi]));
                     CU(cudaStreamWaitEvent(sl.compute, sl.pjoin[gi], 0));
                 }
-            if (g == 0) CU(cudaEventRecord(e2, sl.compute));
+            if (g == 0) { cudaEvent_t e2 = timing_event(sl); CU(cudaEventRecord(e2, sl.compute)); }
 
             if (!out_dev) {
                 /* PCM home over PCIe on the copy stream while the next slab renders */
@@ -860,11 +870,11 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         if (want_log)
             CU(cudaMemcpyAsync(b.log->rec + log_lo, sl.log.p, (log_hi - log_lo) * sizeof(vs_period_rec), cudaMemcpyDeviceToHost, sl.compute));
         if (want_log && b.log->count)
-            CU(cudaMemcpyAsync(sl.h_nper.p, sl.nper.p, ns * sizeof(uint32_t), cudaMemcpyDeviceToHost, sl.compute));
-        CU(cudaMemcpyAsync(sl.h_status.p, sl.status.p, sizeof(int32_t), cudaMemcpyDeviceToHost, sl.compute));
+            CU(cudaMemcpyAsync(sl.h_nper[cp].p, sl.nper[cp].p, ns * sizeof(uint32_t), cudaMemcpyDeviceToHost, sl.compute));
+        CU(cudaMemcpyAsync(sl.h_status[cp].p, sl.status[cp].p, sizeof(int32_t), cudaMemcpyDeviceToHost, sl.compute));
         if (!out_dev) sl.scratch_parity = (unsigned)((sl.scratch_parity + n_slabs) & 1);
         if (g == 0) { cudaEvent_t t_last = timing_event(sl); CU(cudaEventRecord(t_last, sl.compute)); }
-        CU(cudaEventRecord(sl.h2d_done, sl.compute));                 /* "call done" for this slot */
+        CU(cudaEventRecord(sl.call_done[cp], sl.compute));            /* parity-cp buffers are free once this fires */
     }
 
     prof.mark("launches enqueued");
@@ -878,7 +888,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         if (want_log && b.log->count) {
             for (size_t g = 0; g < nslots; g++) {
                 const size_t s0 = cut[g], s1 = cut[g + 1];
-                if (s1 > s0) memcpy(b.log->count + s0, ctx->slots[g].h_nper.p, (s1 - s0) * sizeof(uint32_t));
+                if (s1 > s0) memcpy(b.log->count + s0, ctx->slots[g].h_nper[ctx->slots[g].call_parity ^ 1u].p, (s1 - s0) * sizeof(uint32_t));
             }
         }
     }
@@ -949,7 +959,11 @@ int vs_ctx_create(vs_ctx **out, const int *devices, int n_devices, uint32_t flag
         bool ok = cudaSetDevice(d) == cudaSuccess &&
                   cudaStreamCreateWithFlags(&s.compute, cudaStreamNonBlocking) == cudaSuccess &&
                   cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking) == cudaSuccess &&
-                  cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&s.plan, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&s.call_done[0], cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&s.call_done[1], cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&s.plan_done[0], cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&s.plan_done[1], cudaEventDisableTiming) == cudaSuccess &&
                   cudaEventCreateWithFlags(&s.slab_done[0], cudaEventDisableTiming) == cudaSuccess &&
                   cudaEventCreateWithFlags(&s.slab_done[1], cudaEventDisableTiming) == cudaSuccess &&
                   cudaEventCreateWithFlags(&s.slab_ready, cudaEventDisableTiming) == cudaSuccess &&
@@ -974,13 +988,20 @@ void vs_ctx_destroy(vs_ctx *ctx)
         cudaSetDevice(s.dev);
         if (s.compute) cudaStreamSynchronize(s.compute);
         if (s.copy) cudaStreamSynchronize(s.copy);
-        DevBuf *bufs[] = {&s.streams, &s.chunks, &s.order, &s.table, &s.snap, &s.nper, &s.costab, &s.coef, &s.status,
+        if (s.plan) cudaStreamSynchronize(s.plan);
+        DevBuf *bufs[] = {&s.streams[0], &s.streams[1], &s.chunks[0], &s.chunks[1], &s.order[0], &s.order[1], &s.table[0], &s.table[1],
+                          &s.snap[0], &s.snap[1], &s.nper[0], &s.nper[1], &s.status[0], &s.status[1], &s.costab, &s.coef,
                           &s.pcm[0], &s.pcm[1], &s.raw[0], &s.raw[1], &s.flowin[0], &s.flowin[1], &s.log};
         for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
-        PinBuf *pins[] = {&s.h_streams, &s.h_chunks, &s.h_order, &s.h_nper, &s.h_status};
+        PinBuf *pins[] = {&s.h_streams[0], &s.h_streams[1], &s.h_chunks[0], &s.h_chunks[1], &s.h_order[0], &s.h_order[1],
+                          &s.h_nper[0], &s.h_nper[1], &s.h_status[0], &s.h_status[1]};
         for (PinBuf *b : pins) if (b->p) cudaFreeHost(b->p);
         for (cudaEvent_t e : s.tev) cudaEventDestroy(e);
-        if (s.h2d_done) cudaEventDestroy(s.h2d_done);
+        for (int k = 0; k < 2; k++) {
+            if (s.call_done[k]) cudaEventDestroy(s.call_done[k]);
+            if (s.plan_done[k]) cudaEventDestroy(s.plan_done[k]);
+        }
+        if (s.plan) cudaStreamDestroy(s.plan);
         if (s.slab_done[0]) cudaEventDestroy(s.slab_done[0]);
         if (s.slab_done[1]) cudaEventDestroy(s.slab_done[1]);
         if (s.slab_ready) cudaEventDestroy(s.slab_ready);
@@ -1031,20 +1052,21 @@ int vs_sync(vs_ctx *ctx)
     int status = 0;
     for (Slot &s : ctx->slots) {
         CU(cudaSetDevice(s.dev));
+        CU(cudaStreamSynchronize(s.plan));
         CU(cudaStreamSynchronize(s.compute));
         CU(cudaStreamSynchronize(s.copy));
-        if (s.h_status.p && *(int32_t *)s.h_status.p) { status = *(int32_t *)s.h_status.p; *(int32_t *)s.h_status.p = 0; }
+        for (int k = 0; k < 2; k++)
+            if (s.h_status[k].p && *(int32_t *)s.h_status[k].p) { status = *(int32_t *)s.h_status[k].p; *(int32_t *)s.h_status[k].p = 0; }
     }
     if (ctx->timing_pending) {
         Slot &s = ctx->slots[0];
         ctx->timing_pending = false;
-        if (s.tev_used >= 2) {
-            /* layout: t_first, then (e0,e1,e2) per slab, then t_last */
+        if (s.tev_used >= 3) {
+            /* layout: t_first, t_plan (plan stream), then (e1,e2) per slab, then t_last (compute stream) */
             float ms = 0.0f;
-            for (size_t k = 1; k + 3 <= s.tev_used - 1; k += 3) {
-                if (cudaEventElapsedTime(&ms, s.tev[k], s.tev[k + 1]) == cudaSuccess) ctx->timing.plan_ms += ms;
-                if (cudaEventElapsedTime(&ms, s.tev[k + 1], s.tev[k + 2]) == cudaSuccess) ctx->timing.render_ms += ms;
-            }
+            if (cudaEventElapsedTime(&ms, s.tev[0], s.tev[1]) == cudaSuccess) ctx->timing.plan_ms = ms;
+            for (size_t k = 2; k + 1 < s.tev_used - 1; k += 2)
+                if (cudaEventElapsedTime(&ms, s.tev[k], s.tev[k + 1]) == cudaSuccess) ctx->timing.render_ms += ms;
             if (cudaEventElapsedTime(&ms, s.tev[0], s.tev[s.tev_used - 1]) == cudaSuccess) ctx->timing.total_ms = ms;
             cudaGetLastError();
         }

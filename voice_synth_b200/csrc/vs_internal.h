@@ -6,7 +6,9 @@
 
 #define VS_ORDER   22          /* vowel_new.c:172 */
 #define VS_RING    24          /* state ring / samples per unrolled filter block (>= VS_ORDER, 3 x 16 B of PCM) */
-#define VS_NT      128         /* threads per CTA of the plan and render kernels */
+#define VS_NT      128         /* rows per CTA of the render kernel (and its RNG stride)           */
+#define VS_PLAN_NT 32          /* threads per CTA of the plan kernel: one warp, so that its 128 CTAs
+                                  spread over all SMs and co-reside with render CTAs                */
 #define VS_RNG_DEG 31          /* glibc TYPE_3 */
 #define VS_NO_CHUNK 0xffffffffu
 #define VS_WIN     192         /* samples per stream per render window (8 ring blocks, 24 x 16 B)  */

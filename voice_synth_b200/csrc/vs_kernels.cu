@@ -79,15 +79,17 @@ struct VsRng {
     int f;         /* front index; back index is f-3 (mod 31) */
 };
 
+template <int STRIDE = VS_NT>
 __device__ __forceinline__ int32_t vs_rng_next(VsRng &g)
 {
     const int b = g.f >= 3 ? g.f - 3 : g.f + 28;
-    const uint32_t v = g.r[g.f * VS_NT] + g.r[b * VS_NT];
-    g.r[g.f * VS_NT] = v;
+    const uint32_t v = g.r[g.f * STRIDE] + g.r[b * STRIDE];
+    g.r[g.f * STRIDE] = v;
     g.f = (g.f == VS_RNG_DEG - 1) ? 0 : g.f + 1;
     return (int32_t)(v >> 1);
 }
 
+template <int STRIDE = VS_NT>
 __device__ void vs_rng_seed(VsRng &g, uint32_t seed)
 {
     int32_t w = (int32_t)(seed ? seed : 1u);
@@ -96,18 +98,19 @@ __device__ void vs_rng_seed(VsRng &g, uint32_t seed)
         const int32_t hi = w / 127773, lo = w % 127773;
         w = 16807 * lo - 2836 * hi;
         if (w < 0) w += 2147483647;
-        g.r[i * VS_NT] = (uint32_t)w;
+        g.r[i * STRIDE] = (uint32_t)w;
     }
     g.f = 3;
-    for (int i = 0; i < 310; i++) (void)vs_rng_next(g);
+    for (int i = 0; i < 310; i++) (void)vs_rng_next<STRIDE>(g);
 }
 
 /* store / load the state in canonical rotation (oldest word first => f = 3 after loading) */
+template <int STRIDE = VS_NT>
 __device__ void vs_rng_save(const VsRng &g, uint32_t *dst)
 {
     int j = g.f >= 3 ? g.f - 3 : g.f + 28;
     for (int k = 0; k < VS_RNG_DEG; k++) {
-        dst[k] = g.r[j * VS_NT];
+        dst[k] = g.r[j * STRIDE];
         j = (j == VS_RNG_DEG - 1) ? 0 : j + 1;
     }
 }
@@ -147,15 +150,15 @@ __device__ __forceinline__ int vs_add_clip(int x, int w)
  * PLAN: one thread per stream
  * ============================================================================================== */
 template <bool LOG>
-__global__ void __launch_bounds__(VS_NT) vs_plan_kernel(const VsPlanArgs a)
+__global__ void __launch_bounds__(VS_PLAN_NT) vs_plan_kernel(const VsPlanArgs a)
 {
-    __shared__ uint32_t s_rng[VS_RNG_DEG * VS_NT];
-    const uint32_t s = blockIdx.x * VS_NT + threadIdx.x;
+    __shared__ uint32_t s_rng[VS_RNG_DEG * VS_PLAN_NT];
+    const uint32_t s = blockIdx.x * VS_PLAN_NT + threadIdx.x;
     if (s >= a.n_streams) return;
     const VsStream st = a.streams[s];
     VsRng g;
     g.r = s_rng + threadIdx.x;
-    vs_rng_seed(g, st.seed);                                             /* flowgen_shimmer.c:241 */
+    vs_rng_seed<VS_PLAN_NT>(g, st.seed);                                             /* flowgen_shimmer.c:241 */
 
     const bool do_jit = (st.flags & VS_F_JITTER) && st.jitter != 0.0f;    /* :248 */
     const bool do_shm = (st.flags & VS_F_SHIMMER) && st.shimmer != 0.0f;  /* :295 */
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(VS_NT) vs_plan_kernel(const VsPlanArgs a)
             const double prev = (double)dper;
             float cur;
             do {
-                const int32_t r = vs_rng_next(g); nd++;
+                const int32_t r = vs_rng_next<VS_PLAN_NT>(g); nd++;
                 double t = vs_div_const((double)r, VS_RM4, VS_INV_RM4);
                 t = __dmul_rn(__dmul_rn(t, 40000.0), jit);
                 const double J = (double)__double2float_rn(__dsub_rn(t, jit2));
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(VS_NT) vs_plan_kernel(const VsPlanArgs a)
             const double prev = (double)dsh;
             float cur;
             do {
-                const int32_t r = vs_rng_next(g); nd++;
+                const int32_t r = vs_rng_next<VS_PLAN_NT>(g); nd++;
                 const float eps = __fmul_rn((float)r, 4.656612873077393e-10f);   /* / (float)RAND_MAX == * 2^-31, exact */
                 S = __double2float_rn(__dsub_rn(__dmul_rn(__dmul_rn((double)eps, 4.0), shm), shm2));
                 const double den = __dsub_rn(2.0, (double)S);
@@ -222,14 +225,14 @@ __global__ void __launch_bounds__(VS_NT) vs_plan_kernel(const VsPlanArgs a)
         if (T < 1 || T > 32767) { atomicExch(a.status, VS_ERANGE); return; }
 
         /* closure-speed draw, always consumed (:325) */
-        const int32_t rk = vs_rng_next(g); nd++;
+        const int32_t rk = vs_rng_next<VS_PLAN_NT>(g); nd++;
         const double kq = __dsub_rn(vs_div_const((double)rk, VS_RAND_MAX_D, VS_INV_RM), 0.5);
         const float Knew = __double2float_rn(__dmul_rn(Kbase, __dadd_rn(1.0, __dmul_rn(kv2, kq))));
 
         /* chunks whose generation starts inside this period: remember where we are */
         while (next_target < count + (uint32_t)T) {
             chunks[next_c].first_period = np;
-            if (noise && a.rng_snap) vs_rng_save(g, a.rng_snap + (size_t)(st.chunk0 + next_c) * 32);
+            if (noise && a.rng_snap) vs_rng_save<VS_PLAN_NT>(g, a.rng_snap + (size_t)(st.chunk0 + next_c) * 32);
             next_c++;
             next_target = next_c < st.n_chunks ? chunks[next_c].gen_target : 0xffffffffu;
         }
@@ -270,12 +273,12 @@ __global__ void __launch_bounds__(VS_NT) vs_plan_kernel(const VsPlanArgs a)
                 if (LOG) {
                     float wa = 0.0f;
                     for (uint32_t k = 0; k < n_noise; k++) {
-                        const int w = vs_noise_w(vs_rng_next(g), ndw);
+                        const int w = vs_noise_w(vs_rng_next<VS_PLAN_NT>(g), ndw);
                         wa = __fadd_rn(wa, __fmul_rn((float)w, (float)w));
                     }
                     w_pow = __fdiv_rn(wa, (float)T);
                 } else {
-                    for (uint32_t k = 0; k < n_noise; k++) (void)vs_rng_next(g);
+                    for (uint32_t k = 0; k < n_noise; k++) (void)vs_rng_next<VS_PLAN_NT>(g);
                 }
             }
         }
@@ -800,9 +803,9 @@ cudaError_t vs_launch_fp64_peak(double *scratch, int blocks, int iters, cudaStre
  * ---------------------------------------------------------------------------------------------- */
 cudaError_t vs_launch_plan(const VsPlanArgs &a, bool want_log, cudaStream_t s)
 {
-    const unsigned grid = (a.n_streams + VS_NT - 1) / VS_NT;
-    if (want_log) vs_plan_kernel<true><<<grid, VS_NT, 0, s>>>(a);
-    else vs_plan_kernel<false><<<grid, VS_NT, 0, s>>>(a);
+    const unsigned grid = (a.n_streams + VS_PLAN_NT - 1) / VS_PLAN_NT;
+    if (want_log) vs_plan_kernel<true><<<grid, VS_PLAN_NT, 0, s>>>(a);
+    else vs_plan_kernel<false><<<grid, VS_PLAN_NT, 0, s>>>(a);
     return cudaGetLastError();
 }
 
