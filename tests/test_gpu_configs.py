@@ -129,3 +129,33 @@ def test_edge_shapes(ctx, vs, oracle):
         ctx.flowgen_batch(bad)
     with pytest.raises(vs.VsError):
         ctx.synth_batch(vs.FlowParams(1), vs.FilterParams(1, "x"))
+
+
+def test_fresh_context_first_call(vs, oracle):
+    """first call on a new context: the cosine tables of ~50 distinct T2 are uploaded right before the plan
+    kernel (a missing stream dependency there once produced garbage tables)"""
+    from voice_synth_b200 import workloads
+    c = vs.Context()
+    try:
+        p, f = workloads.cfg5(n=24576, first=7)
+        pcm, offs, ns = c.synth_batch(p, f)
+        rng = np.random.default_rng(11)
+        _check_sample(oracle, vs, p, f, pcm, offs, ns, sorted(set(rng.integers(0, p.n, 16).tolist())))
+    finally:
+        c.close()
+
+
+def test_calls_of_different_shapes_interleave(ctx, vs, oracle):
+    """alternate batches of different shapes and modes: exercises the parity-double-buffered descriptors,
+    the plan cache and the chunk-plan re-upload logic"""
+    from voice_synth_b200 import workloads
+    pa, fa = workloads.cfg2(n=700)
+    pb, fb = workloads.cfg3(n=300, first=1234)
+    ref_a = ctx.synth_batch(pa, fa)[0].copy()
+    ref_b = ctx.synth_batch(pb, fb)[0].copy()
+    for _ in range(3):
+        assert np.array_equal(ctx.synth_batch(pa, fa)[0], ref_a)
+        ctx.flowgen_batch(pb)
+        assert np.array_equal(ctx.synth_batch(pb, fb)[0], ref_b)
+        assert np.array_equal(ctx.synth_batch(pb, fb)[0], ref_b)
+        ctx.flowgen_batch(pa)

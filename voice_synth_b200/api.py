@@ -311,6 +311,10 @@ class Context:
         return (out, offs, raw) if want_raw is not False else (out, offs)
 
     def synth_batch(self, p, f, out=None, offsets=None, want_raw=False):
+        if out is not None and offsets is None and want_raw is False:
+            # fast path for repeated calls into a caller-owned dense buffer: nothing to size or return
+            self._check(self.L.vs_synth_batch(self.h, C.byref(p._c()), C.byref(f._c()), p.n, _ptr(out), None, None))
+            return out, None, None
         ns = flow_nsamples(p)
         offs_arg, offs, total = self._layout(ns, offsets)
         if out is None:

@@ -72,6 +72,7 @@ struct Slot {
     std::vector<std::vector<PlanGroup>> plan_groups;
     std::vector<size_t> plan_slab_c0, plan_slab_r0;
     uint64_t plan_tab_total = 0, plan_warm_total = 0;
+    uint64_t plan_version = 0, uploaded_version[2] = {~0ull, ~0ull};   /* which plan the device copies of chunks/order hold */
 };
 
 } // namespace
@@ -646,6 +647,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         }
         sl.plan_slab_r0[n_slabs] = order.size();
         sl.plan_sig.swap(sig);
+        sl.plan_version++;
         prof.mark("row order");
         }
         const std::vector<VsChunk> &hc = sl.plan_chunks;
@@ -674,8 +676,12 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         CU(cudaEventSynchronize(sl.call_done[cp]));                   /* the call before the previous one is done with them */
         int rc;
         if ((rc = dev_reserve(ctx, sl, sl.streams[cp], ns * sizeof(VsStream)))) return rc;
-        if ((rc = dev_reserve(ctx, sl, sl.chunks[cp], nc * sizeof(VsChunk)))) return rc;
-        if ((rc = dev_reserve(ctx, sl, sl.order[cp], nrows * sizeof(uint32_t) + 16))) return rc;
+        {
+            const void *pc = sl.chunks[cp].p, *po = sl.order[cp].p;
+            if ((rc = dev_reserve(ctx, sl, sl.chunks[cp], nc * sizeof(VsChunk)))) return rc;
+            if ((rc = dev_reserve(ctx, sl, sl.order[cp], nrows * sizeof(uint32_t) + 16))) return rc;
+            if (pc != sl.chunks[cp].p || po != sl.order[cp].p) sl.uploaded_version[cp] = ~0ull;      /* reallocated */
+        }
         if ((rc = dev_reserve(ctx, sl, sl.nper[cp], ns * sizeof(uint32_t)))) return rc;
         if ((rc = dev_reserve(ctx, sl, sl.status[cp], sizeof(int32_t)))) return rc;
         if (b.mode != VS_MODE_FILTER) {
@@ -684,8 +690,11 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             if ((rc = dev_reserve(ctx, sl, sl.costab, std::max<size_t>(8, ctx->cos_host.size() * sizeof(double))))) return rc;
             if (sl.costab_uploaded != ctx->cos_host.size()) {
                 /* tables only ever grow; a synchronous copy keeps the host vector free to grow again */
+                /* stream-ordered on the plan stream (a plain cudaMemcpy from pageable memory may still be in
+                 * flight when it returns, and non-blocking streams do not order after the legacy stream) */
                 CU(cudaStreamSynchronize(sl.compute));
-                CU(cudaMemcpy(sl.costab.p, ctx->cos_host.data(), ctx->cos_host.size() * sizeof(double), cudaMemcpyHostToDevice));
+                CU(cudaMemcpyAsync(sl.costab.p, ctx->cos_host.data(), ctx->cos_host.size() * sizeof(double), cudaMemcpyHostToDevice, sl.plan));
+                CU(cudaStreamSynchronize(sl.plan));
                 ctx->timing.h2d_bytes += ctx->cos_host.size() * sizeof(double);
                 sl.costab_uploaded = ctx->cos_host.size();
             }
@@ -750,13 +759,22 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 }
             }
         }
-        memcpy(sl.h_chunks[cp].p, hc.data(), nc * sizeof(VsChunk));
-        memcpy(sl.h_order[cp].p, order.data(), nrows * sizeof(uint32_t));
+        /* chunk geometry and row order depend on the batch shape only; the plan kernel rewrites every
+         * chunk's first_period each call.  Re-upload them only when the plan changed. */
+        const bool upload_plan = sl.uploaded_version[cp] != sl.plan_version;
+        if (upload_plan) {
+            memcpy(sl.h_chunks[cp].p, hc.data(), nc * sizeof(VsChunk));
+            memcpy(sl.h_order[cp].p, order.data(), nrows * sizeof(uint32_t));
+        }
         *(int32_t *)sl.h_status[cp].p = 0;
         CU(cudaMemcpyAsync(sl.streams[cp].p, sl.h_streams[cp].p, ns * sizeof(VsStream), cudaMemcpyHostToDevice, sl.plan));
-        CU(cudaMemcpyAsync(sl.chunks[cp].p, sl.h_chunks[cp].p, nc * sizeof(VsChunk), cudaMemcpyHostToDevice, sl.plan));
-        CU(cudaMemcpyAsync(sl.order[cp].p, sl.h_order[cp].p, nrows * sizeof(uint32_t), cudaMemcpyHostToDevice, sl.plan));
-        ctx->timing.h2d_bytes += ns * sizeof(VsStream) + nc * sizeof(VsChunk) + nrows * sizeof(uint32_t);
+        if (upload_plan) {
+            CU(cudaMemcpyAsync(sl.chunks[cp].p, sl.h_chunks[cp].p, nc * sizeof(VsChunk), cudaMemcpyHostToDevice, sl.plan));
+            CU(cudaMemcpyAsync(sl.order[cp].p, sl.h_order[cp].p, nrows * sizeof(uint32_t), cudaMemcpyHostToDevice, sl.plan));
+            sl.uploaded_version[cp] = sl.plan_version;
+            ctx->timing.h2d_bytes += nc * sizeof(VsChunk) + nrows * sizeof(uint32_t);
+        }
+        ctx->timing.h2d_bytes += ns * sizeof(VsStream);
         CU(cudaMemsetAsync(sl.status[cp].p, 0, sizeof(int32_t), sl.plan));
 
         prof.mark("reserve + descriptor upload");
@@ -783,6 +801,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         }
         if (g == 0) { cudaEvent_t t_plan = timing_event(sl); CU(cudaEventRecord(t_plan, sl.plan)); }
         CU(cudaEventRecord(sl.plan_done[cp], sl.plan));
+        if (getenv("VS_DEBUG_SYNCPLAN")) CU(cudaStreamSynchronize(sl.plan));
         CU(cudaStreamWaitEvent(sl.compute, sl.plan_done[cp], 0));
 
         /* ---- compute stream: render (and copy) slab by slab ------------------------------------------ */
@@ -820,10 +839,11 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             ra.pcm_out = d_pcm;
             ra.raw_out = d_raw;
             ra.checked_quant = checked_quant ? 1 : 0;
+            ra.status = (int32_t *)sl.status[cp].p;
             /* one launch per vowel preset (its coefficients travel as kernel parameters); with more
              * than one preset the launches fork onto side streams so that they share the SMs */
             const std::vector<Group> &groups = slab_groups[k];
-            const bool fork = groups.size() > 1;
+            const bool fork = groups.size() > 1 && !getenv("VS_DEBUG_NOFORK");
             if (fork) CU(cudaEventRecord(sl.pfork, sl.compute));
             for (size_t gi = 0; gi < groups.size(); gi++) {
                 const Group &gr = groups[gi];

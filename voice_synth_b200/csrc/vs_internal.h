@@ -88,6 +88,7 @@ struct VsRenderArgs {
     int16_t        *pcm_out;
     double         *raw_out;        /* nullable                                                   */
     int             checked_quant;  /* 1: |waveform| may reach 2^30, use the range-checked quantiser */
+    int32_t        *status;         /* device error flag (shared with the plan kernel)              */
 };
 
 #endif

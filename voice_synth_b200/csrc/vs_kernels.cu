@@ -319,6 +319,8 @@ struct __align__(16) VsLane {
     const int16_t *fin;
     int32_t nstart, lo, hi, blk0;
     int32_t T2, DCi, DCs, noise;
+    uint32_t tab_cap;        /* entries of the row's period table: indices are checked against it */
+    uint32_t pad[3];
 };
 
 struct VsEnt {               /* a period-table entry in registers */
@@ -414,6 +416,7 @@ __device__ __forceinline__ void vs_draw_window(const VsLane &me, int w, VsRng &g
     for (int m = mlo; m < mhi; m++) {
         int i = m - re.start;
         while (i >= re.T) {                                   /* next period: its perturbation and K */
+            if (rq + 1 >= me.tab_cap) return;                 /* never walk past the row's table      */
             re = vs_load_entry(me.tab + (++rq));              /* draws come first (:283,:298,:325)   */
             for (int k = 0; k < re.npert; k++) (void)vs_rng_next(g);
             i = m - re.start;
@@ -430,7 +433,6 @@ __device__ __forceinline__ void vs_draw_window(const VsLane &me, int w, VsRng &g
  * work items (one item = 32 consecutive open-phase samples of one segment).  The warp then evaluates
  * four items per step, straight-line, so that four table loads and FP64 chains are in flight. */
 #define VS_ITEM(row, seg, grp) ((uint16_t)((row) | ((seg) << 5) | ((grp) << 7)))
-#define VS_NULL_ITEM VS_ITEM(0, 0, 7)          /* group 7 starts at a0+224 > any window: evaluates nothing */
 #define VS_MAXITEMS (32 * VS_MAXSEG * 7 + 4)
 
 template <int MODE, bool NOISE>
@@ -488,6 +490,7 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
             const int open_end = 2 * mine.T2;
 #pragma unroll 1
             for (int sidx = 0; sidx < VS_MAXSEG; sidx++) {
+                if (q >= mine.tab_cap) { pending = false; break; }          /* never walk past the row's table */
                 const VsEnt e = vs_load_entry(mine.tab + q);
                 const int pend = e.start + e.T;
                 if (pend > glo) {
@@ -523,11 +526,14 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
         const int total = __shfl_sync(VS_FULL, incl, 31);
         {
             int pos = incl - ngrp;
+            uint16_t last = 0;
             for (int sidx = 0; sidx < n; sidx++) {
                 const int gcnt = (int)((grp_counts >> (4 * sidx)) & 15u);
-                for (int gi = 0; gi < gcnt; gi++) items[pos++] = VS_ITEM(myrow, sidx, gi);
+                for (int gi = 0; gi < gcnt; gi++) { last = VS_ITEM(myrow, sidx, gi); items[pos++] = last; }
             }
-            if (lane < 4) items[total + lane] = VS_NULL_ITEM;       /* pad to a multiple of 4 */
+            /* pad to a multiple of 4 with copies of the last item: re-evaluating it is idempotent, so the
+             * evaluation loop needs no validity test */
+            if (ngrp > 0 && incl == total) { items[total] = last; items[total + 1] = last; items[total + 2] = last; }
         }
         __syncwarp();
 
@@ -537,10 +543,10 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
                 const int it = items[b + r];
                 const int row = it & 31;
                 const VsSeg sg = segs[row * VS_MAXSEG + ((it >> 5) & 3)];
-                const int T2 = lanes[row].T2, DCi = lanes[row].DCi;
-                const double *tab = lanes[row].ct;                  /* h[0..T2) then c[0..T2) */
+                const int T2 = lanes[row].T2, DCi = lanes[row].DCi;       /* T2 >= 1: the row has open-phase samples */
+                const double *tab = lanes[row].ct;                        /* h[0..T2) then c[0..T2) */
                 const int o1 = min(sg.a1, 2 * T2);
-                const int i = sg.a0 + (it >> 7) * 32 + lane;
+                const int i = sg.a0 + (it >> 7) * 32 + lane;              /* >= a0 >= 0 */
                 const double tv = __ldg(tab + min(i, 2 * T2 - 1));
                 const double fall = __dadd_rn(__dsub_rn(__dmul_rn(sg.Kd, tv), sg.Kd), 1.0);
                 const int v = vs_ceil_s16(__dmul_rn(sg.Ad, i < T2 ? tv : fall));
@@ -676,7 +682,8 @@ vs_render_kernel(const VsRenderArgs a)
     double *rrow = nullptr;
     VsLane me;
     me.tab = nullptr; me.ct = nullptr; me.orow = nullptr; me.fin = nullptr;
-    me.nstart = 0; me.lo = 0; me.hi = 0; me.blk0 = 0; me.T2 = 0; me.DCi = 0; me.DCs = 0; me.noise = 0;
+    me.nstart = 0; me.lo = 0; me.hi = 0; me.blk0 = 0; me.T2 = 0; me.DCi = 0; me.DCs = 0; me.noise = 0; me.tab_cap = 0;
+    me.pad[0] = me.pad[1] = me.pad[2] = 0;
     if (active) {
         const VsChunk ck = a.chunks[chunk_id];
         const VsStream st = a.streams[ck.stream];
@@ -692,7 +699,12 @@ vs_render_kernel(const VsRenderArgs a)
             me.DCi = (int)ceilf(st.DC);
             me.DCs = st.DCs;
             me.noise = (st.flags & VS_F_NOISE) ? 1 : 0;
+            me.tab_cap = st.tab_cap;
             q = ck.first_period;
+            if (q >= st.tab_cap) {                    /* the plan kernel did not reach this chunk: refuse to walk garbage */
+                atomicExch(a.status, VS_ECUDA);
+                q = 0; me.hi = 0; me.lo = 0;
+            }
             me.nstart = (int)__ldg(&me.tab[q].start);
         }
         const int phase = (int)((reinterpret_cast<uintptr_t>(me.orow) >> 1) & 7);
