@@ -383,20 +383,22 @@ __device__ __forceinline__ int vs_quant_fast_nocheck(double v)
 #define VS_TILE_I16  (32 * VS_TS)
 #define VS_THREADS_PAIRED ((VS_NP + VS_NP * VS_PW) * 32)
 
-/* one pitch period's share of one row's window: what the cooperative evaluation needs */
+/* one pitch period's share of one row's window: everything the cooperative evaluation needs (48 B) */
 struct __align__(16) VsSeg {
     double Ad, Kd;
-    int rel;          /* tile index of the period's sample 0 (may be negative) */
-    int a0, a1;       /* in-period indices [a0,a1) that fall into this window  */
-    uint32_t T34;     /* T3 | T4<<16 (noise) */
+    const double *tab;   /* h[0..T2) then c[0..T2) of the row's T2 */
+    int16_t *out;        /* tile address of the period's sample 0 (only in-window indices are touched) */
+    int a0, a1;          /* in-period indices [a0,a1) that fall into this window  */
+    int T2, DCi;
 };
+#define VS_ITEM_SAMPLES 64                 /* open-phase samples per work item: two per lane */
 
 /* NTILE = tiles per group: 2 (double buffer) in the filtering modes, 1 in flow mode */
 #define VS_SMEM_TILES(NTILE) (VS_NP * (NTILE) * VS_TILE_I16 * 2)
 #define VS_SMEM_LANES (VS_NP * 32 * (int)sizeof(VsLane))
 #define VS_SMEM_SEGS  (VS_NP * 32 * VS_MAXSEG * (int)sizeof(VsSeg))
-#define VS_SMEM_NSEG  (VS_NP * 32 * 4)
-#define VS_ITEMS_BYTES (((32 * VS_MAXSEG * 7 + 4) * 2 + 15) & ~15)      /* work-item list of one producer warp */
+#define VS_SMEM_NSEG  (VS_NP * 32 * 4 + VS_NP * 32 * VS_MAXSEG * 4)   /* per-row segment counts + T3|T4 per segment (noise) */
+#define VS_ITEMS_BYTES (((32 * VS_MAXSEG * 4 + 4) * 2 + 15) & ~15)      /* work-item list of one producer warp */
 #define VS_SMEM_ITEMS(NPROD) (VS_NP * (NPROD) * VS_ITEMS_BYTES)
 #define VS_SMEM_BASE(NTILE) (VS_SMEM_TILES(NTILE) + VS_SMEM_LANES + VS_SMEM_SEGS + VS_SMEM_NSEG + VS_SMEM_ITEMS((NTILE) == 2 ? VS_PW : 1))
 /* noise: RNG states [31][VS_NT] words + the window's noise samples [NP][32][VS_WIN] int16 */
@@ -432,8 +434,7 @@ __device__ __forceinline__ void vs_draw_window(const VsLane &me, int w, VsRng &g
  * period table, queues segment descriptors in shared memory and expands them into a flat list of
  * work items (one item = 32 consecutive open-phase samples of one segment).  The warp then evaluates
  * four items per step, straight-line, so that four table loads and FP64 chains are in flight. */
-#define VS_ITEM(row, seg, grp) ((uint16_t)((row) | ((seg) << 5) | ((grp) << 7)))
-#define VS_MAXITEMS (32 * VS_MAXSEG * 7 + 4)
+#define VS_ITEM(row, seg, grp) ((uint16_t)(((row) * VS_MAXSEG + (seg)) | ((grp) << 7)))
 
 template <int MODE, bool NOISE>
 __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, VsSeg *segs, int *nsegs, uint16_t *items,
@@ -442,6 +443,7 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
 {
     const int myrow = row0 + lane * step;
     const bool have_row = myrow < 32;
+    uint32_t *t34 = reinterpret_cast<uint32_t *>(nsegs + 32);      /* [32][VS_MAXSEG] T3|T4 per queued segment (noise) */
 
     if (MODE == VS_MODE_FILTER) {
         for (int j = row0; j < 32; j += step) {
@@ -498,10 +500,12 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
                     const int nopen = min(a1, open_end) - a0;
                     if (nopen > 0 || (NOISE && mine.noise)) {
                         VsSeg sg;
-                        sg.Ad = e.Ad; sg.Kd = e.Kd; sg.rel = e.start - wb_m; sg.a0 = a0; sg.a1 = a1;
-                        sg.T34 = (uint32_t)e.T3 | ((uint32_t)e.T4 << 16);
+                        sg.Ad = e.Ad; sg.Kd = e.Kd; sg.tab = mine.ct;
+                        sg.out = tile + myrow * VS_TS + (e.start - wb_m);
+                        sg.a0 = a0; sg.a1 = a1; sg.T2 = mine.T2; sg.DCi = mine.DCi;
                         my[n] = sg;
-                        const int gcnt = nopen > 0 ? (nopen + 31) >> 5 : 0;
+                        if (NOISE) t34[myrow * VS_MAXSEG + n] = (uint32_t)e.T3 | ((uint32_t)e.T4 << 16);
+                        const int gcnt = nopen > 0 ? (nopen + VS_ITEM_SAMPLES - 1) / VS_ITEM_SAMPLES : 0;
                         grp_counts |= (uint32_t)gcnt << (4 * n);
                         ngrp += gcnt;
                         n++;
@@ -541,16 +545,17 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 const int it = items[b + r];
-                const int row = it & 31;
-                const VsSeg sg = segs[row * VS_MAXSEG + ((it >> 5) & 3)];
-                const int T2 = lanes[row].T2, DCi = lanes[row].DCi;       /* T2 >= 1: the row has open-phase samples */
-                const double *tab = lanes[row].ct;                        /* h[0..T2) then c[0..T2) */
-                const int o1 = min(sg.a1, 2 * T2);
-                const int i = sg.a0 + (it >> 7) * 32 + lane;              /* >= a0 >= 0 */
-                const double tv = __ldg(tab + min(i, 2 * T2 - 1));
-                const double fall = __dadd_rn(__dsub_rn(__dmul_rn(sg.Kd, tv), sg.Kd), 1.0);
-                const int v = vs_ceil_s16(__dmul_rn(sg.Ad, i < T2 ? tv : fall));
-                if (i < o1 && v >= DCi) tile[row * VS_TS + sg.rel + i] = (int16_t)v;
+                const VsSeg sg = segs[it & 127];                          /* row*VS_MAXSEG + segment */
+                const int o1 = min(sg.a1, 2 * sg.T2);                     /* T2 >= 1: the row has open-phase samples */
+                const int i0 = sg.a0 + (it >> 7) * VS_ITEM_SAMPLES + lane; /* >= a0 >= 0 */
+#pragma unroll
+                for (int u = 0; u < VS_ITEM_SAMPLES / 32; u++) {
+                    const int i = i0 + 32 * u;
+                    const double tv = __ldg(sg.tab + min(i, 2 * sg.T2 - 1));
+                    const double fall = __dadd_rn(__dsub_rn(__dmul_rn(sg.Kd, tv), sg.Kd), 1.0);
+                    const int v = vs_ceil_s16(__dmul_rn(sg.Ad, i < sg.T2 ? tv : fall));
+                    if (i < o1 && v >= sg.DCi) sg.out[i] = (int16_t)v;
+                }
             }
         }
 
@@ -563,10 +568,12 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
                 const int16_t *nrow = noisebuf + j * VS_WIN;
                 for (int sidx = 0; sidx < cnt; sidx++) {
                     const VsSeg sg = segs[j * VS_MAXSEG + sidx];
-                    const int T3 = (int)(sg.T34 & 0xffffu), T4 = (int)(sg.T34 >> 16);
+                    const uint32_t tt = t34[j * VS_MAXSEG + sidx];
+                    const int T3 = (int)(tt & 0xffffu), T4 = (int)(tt >> 16);
+                    const int rel = (int)(sg.out - trow);
                     for (int i = sg.a0 + lane; i < sg.a1; i += 32)
                         if (i < T4 || i >= T3)
-                            trow[sg.rel + i] = (int16_t)vs_add_clip(trow[sg.rel + i], nrow[sg.rel + i]);
+                            trow[rel + i] = (int16_t)vs_add_clip(trow[rel + i], nrow[rel + i]);
                 }
             }
         }
@@ -665,7 +672,7 @@ vs_render_kernel(const VsRenderArgs a)
     int16_t *tile0 = s_tiles + pair * NTILE * VS_TILE_I16;
     VsLane *lanes = s_lanes + pair * 32;
     VsSeg *segs = s_segs + pair * 32 * VS_MAXSEG;
-    int *nsegs = s_nseg + pair * 32;
+    int *nsegs = s_nseg + pair * (32 + 32 * VS_MAXSEG);
     int16_t *noisebuf = s_noise + pair * 32 * VS_WIN;
     uint16_t *items = reinterpret_cast<uint16_t *>(s_items + (pair * (PAIRED ? VS_PW : 1) + (prod > 0 ? prod : 0)) * VS_ITEMS_BYTES);
     const int group_threads = (1 + VS_PW) * 32;
