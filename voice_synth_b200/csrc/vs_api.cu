@@ -34,6 +34,10 @@ cudaError_t vs_launch_fp64_peak(double *scratch, int blocks, int iters, cudaStre
 
 namespace {
 
+/* calls in flight per device slot: descriptors, tables and staging of call k+2 are prepared while call k
+ * renders and the plan kernel of call k+1 runs */
+#define VS_DEPTH 3
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -50,15 +54,16 @@ struct Slot {
     bool own_compute = true;
     cudaStream_t copy = nullptr;
     cudaStream_t plan = nullptr;                     /* descriptor upload + plan kernel of call k+1 overlap render(k) */
-    cudaEvent_t call_done[2] = {nullptr, nullptr};   /* everything of the call that used parity p has finished (compute) */
-    cudaEvent_t plan_done[2] = {nullptr, nullptr};
+    cudaEvent_t call_done[VS_DEPTH] = {};            /* everything of the call that used ring slot p has finished (compute) */
+    cudaEvent_t plan_done[VS_DEPTH] = {};
     unsigned call_parity = 0;
     cudaEvent_t slab_done[2] = {nullptr, nullptr};   /* D2H of the slab using pcm[k] finished */
     cudaEvent_t slab_ready = nullptr;                /* render of the current slab finished   */
     cudaStream_t pstream[VS_NUM_PRESETS] = {};       /* one side stream per vowel preset: the per-preset   */
     cudaEvent_t pfork = nullptr, pjoin[VS_NUM_PRESETS] = {};   /* render launches of a slab run concurrently */
-    DevBuf streams[2], chunks[2], order[2], table[2], snap[2], nper[2], status[2], costab, coef, pcm[2], raw[2], flowin[2], log;
-    PinBuf h_streams[2], h_chunks[2], h_order[2], h_nper[2], h_status[2];
+    DevBuf streams[VS_DEPTH], chunks[VS_DEPTH], order[VS_DEPTH], table[VS_DEPTH], snap[VS_DEPTH], nper[VS_DEPTH], status[VS_DEPTH];
+    DevBuf costab, coef, pcm[2], raw[2], flowin[2], log;
+    PinBuf h_streams[VS_DEPTH], h_chunks[VS_DEPTH], h_order[VS_DEPTH], h_nper[VS_DEPTH], h_status[VS_DEPTH];
     size_t costab_uploaded = 0;
     std::vector<cudaEvent_t> tev;                    /* timing events (slot 0 only) */
     size_t tev_used = 0;
@@ -72,7 +77,7 @@ struct Slot {
     std::vector<std::vector<PlanGroup>> plan_groups;
     std::vector<size_t> plan_slab_c0, plan_slab_r0;
     uint64_t plan_tab_total = 0, plan_warm_total = 0;
-    uint64_t plan_version = 0, uploaded_version[2] = {~0ull, ~0ull};   /* which plan the device copies of chunks/order hold */
+    uint64_t plan_version = 1, uploaded_version[VS_DEPTH] = {};        /* which plan the device copies of chunks/order hold (0 = none) */
 };
 
 } // namespace
@@ -88,6 +93,7 @@ struct vs_ctx {
     int opt_async_host = 0;
     std::vector<double> cos_host;
     std::map<int, uint32_t> cos_index;
+    std::vector<uint32_t> cos_fast;      /* T2 -> table offset, direct index in front of the map */
     int warm[VS_NUM_PRESETS];    /* warm-up samples per preset at opt_tol (gain-independent part) */
     double l1gain[VS_NUM_PRESETS]; /* sum |h[n]| of each preset: |y| <= l1gain * gain * max|x| */
     std::string err;
@@ -194,14 +200,16 @@ int row_T2(const FlowRow &r, int P)
     return (int)std::ceil(v);
 }
 
-int row_validate(const FlowRow &r)
+int row_validate(const FlowRow &r, int *P_out = nullptr, uint64_t *n_out = nullptr)
 {
     if (!(r.fs > 0) || !std::isfinite(r.dur) || !(r.dur > 0.0f)) return VS_ERANGE;
     if (!std::isfinite(r.F0) || !(r.F0 > 0.0f)) return VS_ERANGE;
     const int P = row_P(r);
-    if (P < 1 || P > 32000) return VS_ERANGE;                        /* T is stored in a short (:289) */
+    if (P < 1 || P > 27000) return VS_ERANGE;                        /* T <= 1.2*P is stored in a short (:289) */
     const uint64_t n = row_nsamples(r);
     if (n < 1 || n > 0x7fffffffull) return VS_ERANGE;
+    if (P_out) *P_out = P;
+    if (n_out) *n_out = n;
     if (!(r.jitter >= 0.0f && r.jitter <= 10.0f)) return VS_ERANGE;   /* :478 */
     if (!(r.shimmer >= 0.0f && r.shimmer <= 1.0f)) return VS_ERANGE;  /* :544 */
     if (!(r.cq >= 0.0f && r.cq <= 1.0f)) return VS_ERANGE;            /* :490 */
@@ -282,6 +290,7 @@ void compute_warmups(vs_ctx *ctx)
 
 uint32_t cos_table_for(vs_ctx *ctx, int T2)
 {
+    if (T2 >= 0 && (size_t)T2 < ctx->cos_fast.size() && ctx->cos_fast[T2] != 0xffffffffu) return ctx->cos_fast[T2];
     auto it = ctx->cos_index.find(T2);
     if (it != ctx->cos_index.end()) return it->second;
     const uint32_t off = (uint32_t)ctx->cos_host.size();
@@ -303,6 +312,10 @@ uint32_t cos_table_for(vs_ctx *ctx, int T2)
     }
     for (int i = 0; i < T2; i++) ctx->cos_host.push_back(c[i]);
     ctx->cos_index[T2] = off;
+    if (T2 >= 0 && T2 < 65536) {
+        if ((size_t)T2 >= ctx->cos_fast.size()) ctx->cos_fast.resize((size_t)T2 + 64, 0xffffffffu);
+        ctx->cos_fast[T2] = off;
+    }
     return off;
 }
 
@@ -394,7 +407,9 @@ void plan_filter_chunks(vs_ctx *ctx, const Slot &slot, const std::vector<VsStrea
         for (size_t i = 0; i < ns; i++) nchunks[i] = hs[a0 + i].n <= L ? 1u : (uint32_t)((hs[a0 + i].n + L - 1) / L);
         return;
     }
-    const double cap = (double)slot.sm_count * VS_NT;          /* rows per wave */
+    /* rows per wave; a few SMs stay free for the plan kernel of the next call (see VS_PLAN_SMS) */
+    const int render_sms = slot.sm_count > 8 * VS_PLAN_SMS ? slot.sm_count - VS_PLAN_SMS : slot.sm_count;
+    const double cap = (double)render_sms * VS_NT;
     /* streams of equal (length, preset) get equal chunk counts: plan over the distinct classes */
     std::map<std::pair<uint32_t, uint8_t>, uint32_t> classes;
     uint32_t nmax = 0;
@@ -462,10 +477,12 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             s.n = (uint32_t)b.nsamp[i];
         } else {
             const FlowRow r = flow_row(b.fp, i);
-            const int rc = row_validate(r);
+            int P = 0;
+            uint64_t nn = 0;
+            const int rc = row_validate(r, &P, &nn);
             if (rc) return fail(ctx, rc, "stream %zu: flow parameter out of range", i);
-            s.n = (uint32_t)row_nsamples(r);
-            s.P = row_P(r);
+            s.n = (uint32_t)nn;
+            s.P = P;
             s.T2 = row_T2(r, s.P);
             s.cos_off = cos_table_for(ctx, s.T2);
             s.amp = r.amp; s.DC = r.DC; s.jitter = r.jitter; s.shimmer = r.shimmer; s.K = r.K; s.Kvar = r.Kvar;
@@ -672,7 +689,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         /* device memory: descriptor/table buffers alternate between calls (parity cp), so that the
          * upload + plan kernel of this call can run while the previous call still renders */
         const unsigned cp = sl.call_parity;
-        sl.call_parity ^= 1u;
+        sl.call_parity = (sl.call_parity + 1u) % VS_DEPTH;
         CU(cudaEventSynchronize(sl.call_done[cp]));                   /* the call before the previous one is done with them */
         int rc;
         if ((rc = dev_reserve(ctx, sl, sl.streams[cp], ns * sizeof(VsStream)))) return rc;
@@ -680,7 +697,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             const void *pc = sl.chunks[cp].p, *po = sl.order[cp].p;
             if ((rc = dev_reserve(ctx, sl, sl.chunks[cp], nc * sizeof(VsChunk)))) return rc;
             if ((rc = dev_reserve(ctx, sl, sl.order[cp], nrows * sizeof(uint32_t) + 16))) return rc;
-            if (pc != sl.chunks[cp].p || po != sl.order[cp].p) sl.uploaded_version[cp] = ~0ull;      /* reallocated */
+            if (pc != sl.chunks[cp].p || po != sl.order[cp].p) sl.uploaded_version[cp] = 0;          /* reallocated */
         }
         if ((rc = dev_reserve(ctx, sl, sl.nper[cp], ns * sizeof(uint32_t)))) return rc;
         if ((rc = dev_reserve(ctx, sl, sl.status[cp], sizeof(int32_t)))) return rc;
@@ -908,7 +925,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         if (want_log && b.log->count) {
             for (size_t g = 0; g < nslots; g++) {
                 const size_t s0 = cut[g], s1 = cut[g + 1];
-                if (s1 > s0) memcpy(b.log->count + s0, ctx->slots[g].h_nper[ctx->slots[g].call_parity ^ 1u].p, (s1 - s0) * sizeof(uint32_t));
+                if (s1 > s0) memcpy(b.log->count + s0, ctx->slots[g].h_nper[(ctx->slots[g].call_parity + VS_DEPTH - 1u) % VS_DEPTH].p, (s1 - s0) * sizeof(uint32_t));
             }
         }
     }
@@ -980,10 +997,7 @@ int vs_ctx_create(vs_ctx **out, const int *devices, int n_devices, uint32_t flag
                   cudaStreamCreateWithFlags(&s.compute, cudaStreamNonBlocking) == cudaSuccess &&
                   cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking) == cudaSuccess &&
                   cudaStreamCreateWithFlags(&s.plan, cudaStreamNonBlocking) == cudaSuccess &&
-                  cudaEventCreateWithFlags(&s.call_done[0], cudaEventDisableTiming) == cudaSuccess &&
-                  cudaEventCreateWithFlags(&s.call_done[1], cudaEventDisableTiming) == cudaSuccess &&
-                  cudaEventCreateWithFlags(&s.plan_done[0], cudaEventDisableTiming) == cudaSuccess &&
-                  cudaEventCreateWithFlags(&s.plan_done[1], cudaEventDisableTiming) == cudaSuccess &&
+
                   cudaEventCreateWithFlags(&s.slab_done[0], cudaEventDisableTiming) == cudaSuccess &&
                   cudaEventCreateWithFlags(&s.slab_done[1], cudaEventDisableTiming) == cudaSuccess &&
                   cudaEventCreateWithFlags(&s.slab_ready, cudaEventDisableTiming) == cudaSuccess &&
@@ -991,6 +1005,9 @@ int vs_ctx_create(vs_ctx **out, const int *devices, int n_devices, uint32_t flag
                   cudaMalloc(&s.coef.p, coef.size() * sizeof(double)) == cudaSuccess &&
                   cudaMemcpy(s.coef.p, coef.data(), coef.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
         s.coef.cap = coef.size() * sizeof(double);
+        for (int k = 0; ok && k < VS_DEPTH; k++)
+            ok = cudaEventCreateWithFlags(&s.call_done[k], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&s.plan_done[k], cudaEventDisableTiming) == cudaSuccess;
         for (int k = 0; ok && k < VS_NUM_PRESETS; k++)
             ok = cudaStreamCreateWithFlags(&s.pstream[k], cudaStreamNonBlocking) == cudaSuccess &&
                  cudaEventCreateWithFlags(&s.pjoin[k], cudaEventDisableTiming) == cudaSuccess;
@@ -1009,15 +1026,16 @@ void vs_ctx_destroy(vs_ctx *ctx)
         if (s.compute) cudaStreamSynchronize(s.compute);
         if (s.copy) cudaStreamSynchronize(s.copy);
         if (s.plan) cudaStreamSynchronize(s.plan);
-        DevBuf *bufs[] = {&s.streams[0], &s.streams[1], &s.chunks[0], &s.chunks[1], &s.order[0], &s.order[1], &s.table[0], &s.table[1],
-                          &s.snap[0], &s.snap[1], &s.nper[0], &s.nper[1], &s.status[0], &s.status[1], &s.costab, &s.coef,
-                          &s.pcm[0], &s.pcm[1], &s.raw[0], &s.raw[1], &s.flowin[0], &s.flowin[1], &s.log};
+        std::vector<DevBuf *> bufs = {&s.costab, &s.coef, &s.pcm[0], &s.pcm[1], &s.raw[0], &s.raw[1], &s.flowin[0], &s.flowin[1], &s.log};
+        std::vector<PinBuf *> pins;
+        for (int k = 0; k < VS_DEPTH; k++) {
+            for (DevBuf *b : {&s.streams[k], &s.chunks[k], &s.order[k], &s.table[k], &s.snap[k], &s.nper[k], &s.status[k]}) bufs.push_back(b);
+            for (PinBuf *b : {&s.h_streams[k], &s.h_chunks[k], &s.h_order[k], &s.h_nper[k], &s.h_status[k]}) pins.push_back(b);
+        }
         for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
-        PinBuf *pins[] = {&s.h_streams[0], &s.h_streams[1], &s.h_chunks[0], &s.h_chunks[1], &s.h_order[0], &s.h_order[1],
-                          &s.h_nper[0], &s.h_nper[1], &s.h_status[0], &s.h_status[1]};
         for (PinBuf *b : pins) if (b->p) cudaFreeHost(b->p);
         for (cudaEvent_t e : s.tev) cudaEventDestroy(e);
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < VS_DEPTH; k++) {
             if (s.call_done[k]) cudaEventDestroy(s.call_done[k]);
             if (s.plan_done[k]) cudaEventDestroy(s.plan_done[k]);
         }
@@ -1075,7 +1093,7 @@ int vs_sync(vs_ctx *ctx)
         CU(cudaStreamSynchronize(s.plan));
         CU(cudaStreamSynchronize(s.compute));
         CU(cudaStreamSynchronize(s.copy));
-        for (int k = 0; k < 2; k++)
+        for (int k = 0; k < VS_DEPTH; k++)
             if (s.h_status[k].p && *(int32_t *)s.h_status[k].p) { status = *(int32_t *)s.h_status[k].p; *(int32_t *)s.h_status[k].p = 0; }
     }
     if (ctx->timing_pending) {

@@ -7,8 +7,12 @@
 #define VS_ORDER   22          /* vowel_new.c:172 */
 #define VS_RING    24          /* state ring / samples per unrolled filter block (>= VS_ORDER, 3 x 16 B of PCM) */
 #define VS_NT      128         /* rows per CTA of the render kernel (and its RNG stride)           */
-#define VS_PLAN_NT 32          /* threads per CTA of the plan kernel: one warp, so that its 128 CTAs
-                                  spread over all SMs and co-reside with render CTAs                */
+#define VS_PLAN_NT 512         /* threads per CTA of the plan kernel.  With VS_PLAN_SMEM of shared memory a plan
+                                  CTA cannot share an SM with a render CTA: the plan kernel of call k+1 runs on
+                                  the VS_PLAN_SMS SMs the chunk planner keeps free, instead of being starved of
+                                  issue slots by the render warps of call k (measured: 0.35 -> 0.7 ms)        */
+#define VS_PLAN_SMEM (96 * 1024)
+#define VS_PLAN_SMS  8
 #define VS_RNG_DEG 31          /* glibc TYPE_3 */
 #define VS_NO_CHUNK 0xffffffffu
 #define VS_WIN     192         /* samples per stream per render window (8 ring blocks, 24 x 16 B)  */

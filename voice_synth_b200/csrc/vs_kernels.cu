@@ -150,9 +150,9 @@ __device__ __forceinline__ int vs_add_clip(int x, int w)
  * PLAN: one thread per stream
  * ============================================================================================== */
 template <bool LOG>
-__global__ void __launch_bounds__(VS_PLAN_NT) vs_plan_kernel(const VsPlanArgs a)
+__global__ void __launch_bounds__(VS_PLAN_NT, 1) vs_plan_kernel(const VsPlanArgs a)
 {
-    __shared__ uint32_t s_rng[VS_RNG_DEG * VS_PLAN_NT];
+    extern __shared__ __align__(16) uint32_t s_rng[];                  /* [31][VS_PLAN_NT] RNG states (+ padding up to VS_PLAN_SMEM) */
     const uint32_t s = blockIdx.x * VS_PLAN_NT + threadIdx.x;
     if (s >= a.n_streams) return;
     const VsStream st = a.streams[s];
@@ -378,7 +378,7 @@ __device__ __forceinline__ int vs_quant_fast_nocheck(double v)
  * is worked by one CONSUMER warp (F phase; warps 0..NP-1, one per SM sub-partition) and VS_PW
  * PRODUCER warps (G and W phases) over two tiles; in flow mode by a single warp doing G then W.   */
 #define VS_NP        4
-#define VS_PW        5
+#define VS_PW        4
 #define VS_MAXSEG    4                     /* period segments a row can queue per bookkeeping pass */
 #define VS_TILE_I16  (32 * VS_TS)
 #define VS_THREADS_PAIRED ((VS_NP + VS_NP * VS_PW) * 32)
@@ -823,8 +823,14 @@ cudaError_t vs_launch_fp64_peak(double *scratch, int blocks, int iters, cudaStre
 cudaError_t vs_launch_plan(const VsPlanArgs &a, bool want_log, cudaStream_t s)
 {
     const unsigned grid = (a.n_streams + VS_PLAN_NT - 1) / VS_PLAN_NT;
-    if (want_log) vs_plan_kernel<true><<<grid, VS_PLAN_NT, 0, s>>>(a);
-    else vs_plan_kernel<false><<<grid, VS_PLAN_NT, 0, s>>>(a);
+    static_assert(VS_PLAN_SMEM >= VS_RNG_DEG * VS_PLAN_NT * 4, "plan kernel shared memory");
+    if (want_log) {
+        cudaFuncSetAttribute(vs_plan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_PLAN_SMEM);
+        vs_plan_kernel<true><<<grid, VS_PLAN_NT, VS_PLAN_SMEM, s>>>(a);
+    } else {
+        cudaFuncSetAttribute(vs_plan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_PLAN_SMEM);
+        vs_plan_kernel<false><<<grid, VS_PLAN_NT, VS_PLAN_SMEM, s>>>(a);
+    }
     return cudaGetLastError();
 }
 
