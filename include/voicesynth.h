@@ -120,7 +120,6 @@ typedef struct vs_timing {
 #define VS_OPT_EXACT_FILTER    3  /* 1: unfused mul+sub in the reference's order (bit-exact, 2x FP64 work, no chunking) */
 #define VS_OPT_SLAB_STREAMS    4  /* streams per launch/copy slab for host outputs; 0 = auto            */
 #define VS_OPT_TARGET_WARPS    5  /* auto-chunking aims at this many warps per SM sub-partition (2)      */
-#define VS_OPT_LONG_SCAN       6  /* 0/1: allow the exact two-pass carry scan for long streams (1)       */
 #define VS_OPT_ASYNC_HOST      7  /* 1: calls with PINNED host buffers also return after enqueueing; the
                                      PCM of call k crosses PCIe while call k+1 renders (two device
                                      scratch buffers alternate).  vs_sync() before reading.  (0)          */

@@ -159,3 +159,25 @@ def test_calls_of_different_shapes_interleave(ctx, vs, oracle):
         assert np.array_equal(ctx.synth_batch(pb, fb)[0], ref_b)
         assert np.array_equal(ctx.synth_batch(pb, fb)[0], ref_b)
         ctx.flowgen_batch(pa)
+
+
+def test_multi_device_context(vs, oracle):
+    """one vs_ctx over two GPUs: contiguous stream ranges per device, results identical to one device"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from voice_synth_b200 import workloads
+    p, f = workloads.cfg2(n=1536)
+    one = vs.Context(devices=[0])
+    two = vs.Context(devices=[0, 1])
+    try:
+        a, offs, ns = one.synth_batch(p, f)
+        b, _, _ = two.synth_batch(p, f)
+        assert np.abs(a.astype(np.int32) - b.astype(np.int32)).max() <= 1      # chunking differs per device share
+        fa, foffs, _ = one.flowgen_batch(p)
+        fb, _, _ = two.flowgen_batch(p)
+        assert np.array_equal(fa, fb)
+        _check_sample(oracle, vs, p, f, b, offs, ns, [0, 700, 800, 1535], fb, foffs)
+    finally:
+        one.close()
+        two.close()

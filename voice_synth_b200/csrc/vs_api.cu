@@ -89,7 +89,6 @@ struct vs_ctx {
     int opt_exact = 0;
     int opt_slab = 0;
     double opt_warps = 2.0;
-    int opt_long_scan = 1;
     int opt_async_host = 0;
     std::vector<double> cos_host;
     std::map<int, uint32_t> cos_index;
@@ -1066,7 +1065,6 @@ int vs_ctx_set_option(vs_ctx *ctx, int option, double value)
     case VS_OPT_EXACT_FILTER: ctx->opt_exact = value != 0.0; return VS_OK;
     case VS_OPT_SLAB_STREAMS: ctx->opt_slab = value > 0 ? (int)value : 0; return VS_OK;
     case VS_OPT_TARGET_WARPS: if (!(value > 0)) return VS_EINVAL; ctx->opt_warps = value; return VS_OK;
-    case VS_OPT_LONG_SCAN: ctx->opt_long_scan = value != 0.0; return VS_OK;
     case VS_OPT_ASYNC_HOST: ctx->opt_async_host = value != 0.0; return VS_OK;
     default: return VS_EINVAL;
     }
