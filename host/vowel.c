@@ -2,10 +2,8 @@
  * on the GPU through vs_vowel_filter_batch(), WAV out.  Reads both the canonical 44-byte header and
  * the 72-byte one the reference's 64-bit build writes; always writes the canonical one.
  *
- * -n (white noise added to the filtered output, vowel_new.c:302-324) is NOT part of the GPU hot path
- * (SURVEY.md 8f, row N1): this tool applies it on the host after the GPU filter, frame by frame, with
- * the C library's own srandom()/random() exactly as the reference does. */
-#include <math.h>
+ * -n (white noise added to the filtered output, vowel_new.c:302-324) also runs on the
+ * GPU: vs_vowel_noise_batch() on the filtered PCM, seeded like the reference with time() or $VS_SEED. */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -13,34 +11,6 @@
 #include "voicesynth.h"
 #include "vs_cli.h"
 #include "vs_wav.h"
-
-static int16_t round_half_down(double x)            /* vowel_new.c:413-427 */
-{
-    double dec = x - floor(x);
-    if (dec > 0.5) x = x + 1;
-    if (x > 32767) x = 32767; else if (x < -32767) x = -32767;
-    return (int16_t)floor(x);
-}
-
-static void add_output_noise(int16_t *y, size_t n, float snr, uint32_t fs, uint32_t seed)
-{
-    const int ms1 = (int)(fs * 0.001 / 2.0) * 2;
-    const size_t frame = (size_t)(50 * ms1);
-    if (!frame) return;
-    srandom(seed);
-    for (size_t base = 0; base < n; base += frame) {
-        const size_t ni = n - base < frame ? n - base : frame;
-        float acc = 0.0f;
-        for (size_t i = 0; i < ni; i++) acc += (float)y[base + i] * y[base + i];
-        const float power = acc / (float)(short)ni;
-        const float width = sqrt(12 * power / snr);
-        for (size_t i = 0; i < ni; i++) {
-            const float u = (1.0 * random()) / RAND_MAX;
-            const float w = width * (u - 0.5);
-            y[base + i] = round_half_down(1.0 * y[base + i] + 1.0 * w);
-        }
-    }
-}
 
 int main(int argc, char **argv)
 {
@@ -77,7 +47,12 @@ int main(int argc, char **argv)
         rc = vs_vowel_filter_batch(ctx, flow, NULL, &ns, &f, 1, pcm, NULL, NULL);
         if (rc) { fprintf(stderr, "vowel: %s (%s)\n", vs_strerror(rc), vs_last_error(ctx)); return 1; }
     }
-    if (a.has_noise) add_output_noise(pcm, n, a.snr_linear, wi.sample_rate, vs_cli_seed());
+    if (a.has_noise && n) {
+        const uint32_t seed = vs_cli_seed();
+        const int32_t rate = (int32_t)wi.sample_rate;
+        rc = vs_vowel_noise_batch(ctx, pcm, NULL, &ns, &a.snr_linear, &rate, &seed, 1);
+        if (rc) { fprintf(stderr, "vowel: %s (%s)\n", vs_strerror(rc), vs_last_error(ctx)); return 1; }
+    }
     if (fwrite(pcm, sizeof *pcm, n, out) != n) { printf("Error while writing %s\n", a.out_path); return 1; }
     fclose(out);
     free(pcm); free(flow);

@@ -169,6 +169,14 @@ int vs_vowel_filter_batch(vs_ctx *ctx, const int16_t *flow_in, const uint64_t *i
                           const uint64_t *nsamp, const vs_filter_params *f, size_t n,
                           int16_t *pcm_out, const uint64_t *out_offsets, double *raw_out);
 
+/* SURVEY 8f N1 -- `vowel -n`: white noise added to already filtered PCM, IN PLACE (vowel_new.c:302-324).
+ * Per stream and per frame of 50*((int)(fs*0.001/2.0)*2) samples: float power of the frame, uniform
+ * noise of width sqrt(12*power/snr) drawn with random() seeded by srandom(seed[i]) (vowel_new.c:234),
+ * round2int() again.  snr = (float)pow(10, dB/10) as the tool computes it (:143); streams with
+ * snr[i] <= 0 are left untouched.  pcm may be host or device memory. */
+int vs_vowel_noise_batch(vs_ctx *ctx, int16_t *pcm, const uint64_t *offsets, const uint64_t *nsamp,
+                         const float *snr, const int32_t *fs, const uint32_t *seed, size_t n);
+
 /* n voices, flow generation fused with the filter: only the final PCM is written. */
 int vs_synth_batch(vs_ctx *ctx, const vs_flow_params *p, const vs_filter_params *f, size_t n,
                    int16_t *pcm_out, const uint64_t *offsets, double *raw_out);

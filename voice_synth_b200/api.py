@@ -310,6 +310,19 @@ class Context:
                                                  len(ns), _ptr(out), _ptr(out_arg), _ptr(raw)))
         return (out, offs, raw) if want_raw is not False else (out, offs)
 
+    def vowel_noise_batch(self, pcm, nsamp, snr_db, seeds, offsets=None, fs=None):
+        """`vowel -n`: in-place output noise on filtered PCM (vowel_new.c:302-324). snr_db <= 0 leaves a stream alone."""
+        ns = np.ascontiguousarray(nsamp, dtype=np.uint64)
+        n = len(ns)
+        db = np.broadcast_to(np.asarray(snr_db, dtype=np.float32), (n,))
+        snr = np.array([np.float32(math.pow(10.0, float(d / np.float32(10)))) if d > 0 else np.float32(0) for d in db], dtype=np.float32)
+        sd = np.ascontiguousarray(np.broadcast_to(np.asarray(seeds, dtype=np.uint32), (n,)))
+        rate = None if fs is None else np.ascontiguousarray(np.broadcast_to(np.asarray(fs, dtype=np.int32), (n,)))
+        offs = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._check(self.L.vs_vowel_noise_batch(self.h, _ptr(pcm), _ptr(offs), ns.ctypes.data, snr.ctypes.data,
+                                                _ptr(rate), sd.ctypes.data, n))
+        return pcm
+
     def synth_batch(self, p, f, out=None, offsets=None, want_raw=False):
         if out is not None and offsets is None and want_raw is False:
             # fast path for repeated calls into a caller-owned dense buffer: nothing to size or return

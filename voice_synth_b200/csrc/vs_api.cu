@@ -31,6 +31,7 @@ enum { VS_MODE_FLOW = 0, VS_MODE_SYNTH = 1, VS_MODE_FILTER = 2 };
 cudaError_t vs_launch_plan(const VsPlanArgs &a, bool want_log, cudaStream_t s);
 cudaError_t vs_launch_render(const VsRenderArgs &a, int mode, bool noise, bool exact, cudaStream_t s);
 cudaError_t vs_launch_fp64_peak(double *scratch, int blocks, int iters, cudaStream_t s);
+cudaError_t vs_launch_vnoise(int16_t *pcm, const VsNoiseRow *rows, uint32_t n_rows, cudaStream_t s);
 
 namespace {
 
@@ -1201,6 +1202,54 @@ int vs_vowel_filter_batch(vs_ctx *ctx, const int16_t *flow_in, const uint64_t *i
 {
     Batch b = {VS_MODE_FILTER, n, nullptr, f, flow_in, in_offsets, nsamp, pcm_out, out_offsets, raw_out, nullptr};
     return run_batch(ctx, b);
+}
+
+int vs_vowel_noise_batch(vs_ctx *ctx, int16_t *pcm, const uint64_t *offsets, const uint64_t *nsamp, const float *snr,
+                         const int32_t *fs, const uint32_t *seed, size_t n)
+{
+    if (!ctx || !pcm || !nsamp || !snr) return VS_EINVAL;
+    if (n == 0) return VS_OK;
+    if (n > 0x7fffffffull) return fail(ctx, VS_EINVAL, "too many streams");
+    int rc = vs_sync(ctx);                                    /* in-place: earlier work on this PCM must have landed */
+    if (rc) return rc;
+    Slot &sl = ctx->slots[0];
+    CU(cudaSetDevice(sl.dev));
+    std::vector<VsNoiseRow> rows(n);
+    uint64_t max_n = 0, lo = ~0ull, hi = 0;
+    for (size_t i = 0; i < n; i++) max_n = std::max(max_n, nsamp[i]);
+    for (size_t i = 0; i < n; i++) {
+        if (nsamp[i] > 0x7fffffffull) return fail(ctx, VS_EOVERLAP, "stream %zu: too many samples", i);
+        const int32_t rate = fs ? fs[i] : 22050;
+        if (rate <= 0) return fail(ctx, VS_ERANGE, "stream %zu: sampling rate", i);
+        const int ms1 = (int)((uint32_t)rate * 0.001 / 2.0) * 2;       /* vowel_new.c:361 */
+        const long frame = 50L * ms1;                                  /* :363 */
+        if (snr[i] > 0.0f && (frame <= 0 || frame > 32767)) return fail(ctx, VS_ERANGE, "stream %zu: frame length %ld", i, frame);
+        rows[i].off = offsets ? offsets[i] : (uint64_t)i * max_n;
+        rows[i].n = (uint32_t)nsamp[i];
+        rows[i].frame = (uint32_t)frame;
+        rows[i].snr = snr[i];
+        rows[i].seed = seed ? seed[i] : 1u;
+        lo = std::min(lo, rows[i].off);
+        hi = std::max(hi, rows[i].off + rows[i].n);
+    }
+    int dev = -1;
+    const bool on_dev = classify(pcm, &dev) == PK_DEVICE;
+    if (on_dev && dev != sl.dev) return fail(ctx, VS_EINVAL, "device buffer lives on device %d, ctx on %d", dev, sl.dev);
+    if ((rc = dev_reserve(ctx, sl, sl.log, n * sizeof(VsNoiseRow)))) return rc;          /* the log scratch doubles as row storage */
+    CU(cudaMemcpyAsync(sl.log.p, rows.data(), n * sizeof(VsNoiseRow), cudaMemcpyHostToDevice, sl.compute));
+    int16_t *d_pcm = pcm;
+    if (!on_dev) {
+        if ((rc = dev_reserve(ctx, sl, sl.pcm[0], (hi - lo) * sizeof(int16_t) + 64))) return rc;
+        d_pcm = (int16_t *)sl.pcm[0].p - lo;
+        CU(cudaMemcpyAsync(sl.pcm[0].p, pcm + lo, (hi - lo) * sizeof(int16_t), cudaMemcpyHostToDevice, sl.compute));
+    }
+    CU(vs_launch_vnoise(d_pcm, (const VsNoiseRow *)sl.log.p, (uint32_t)n, sl.compute));
+    if (!on_dev)
+        for (size_t i = 0; i < n; i++)                         /* only the rows: gaps between them are not ours */
+            if (rows[i].n && rows[i].snr > 0.0f)
+                CU(cudaMemcpyAsync(pcm + rows[i].off, d_pcm + rows[i].off, rows[i].n * sizeof(int16_t), cudaMemcpyDeviceToHost, sl.compute));
+    CU(cudaStreamSynchronize(sl.compute));                    /* `rows` is pageable host memory */
+    return VS_OK;
 }
 
 int vs_synth_batch(vs_ctx *ctx, const vs_flow_params *p, const vs_filter_params *f, size_t n, int16_t *pcm_out,

@@ -95,4 +95,13 @@ struct VsRenderArgs {
     int32_t        *status;         /* device error flag (shared with the plan kernel)              */
 };
 
+/* vowel -n (N1): one entry per stream */
+struct VsNoiseRow {
+    uint64_t off;          /* samples, relative to the pcm pointer */
+    uint32_t n;
+    uint32_t frame;        /* 50 * ((int)(fs*0.001/2.0)*2), vowel_new.c:361-363 */
+    float    snr;
+    uint32_t seed;
+};
+
 #endif

@@ -796,6 +796,43 @@ vs_render_kernel(const VsRenderArgs a)
     }
 }
 
+/* ================================================================================================
+ * vowel -n: output noise, one thread per stream, in place (vowel_new.c:302-324)
+ * ============================================================================================== */
+__global__ void __launch_bounds__(VS_NT) vs_vnoise_kernel(int16_t *pcm, const VsNoiseRow *rows, uint32_t n_rows)
+{
+    __shared__ uint32_t s_rng[VS_RNG_DEG * VS_NT];
+    const uint32_t s = blockIdx.x * VS_NT + threadIdx.x;
+    if (s >= n_rows) return;
+    const VsNoiseRow r = rows[s];
+    if (!(r.snr > 0.0f) || r.frame == 0) return;
+    VsRng g;
+    g.r = s_rng + threadIdx.x;
+    vs_rng_seed(g, r.seed);                                              /* :234 */
+    int16_t *y = pcm + r.off;
+    for (uint32_t base = 0; base < r.n; base += r.frame) {
+        const uint32_t ni = min(r.frame, r.n - base);
+        float aux = 0.0f;
+        for (uint32_t i = 0; i < ni; i++) {                              /* :304-306, float, in order */
+            const float v = (float)y[base + i];
+            aux = __fadd_rn(aux, __fmul_rn(v, v));
+        }
+        const float sig_power = __fdiv_rn(aux, (float)(int16_t)ni);      /* `ni` is a signed short (:65) */
+        const float width = __double2float_rn(sqrt((double)__fdiv_rn(__fmul_rn(12.0f, sig_power), r.snr)));   /* :309 */
+        for (uint32_t i = 0; i < ni; i++) {                              /* :314-319 */
+            const float nv = __double2float_rn(vs_div_const((double)vs_rng_next(g), VS_RAND_MAX_D, VS_INV_RM));
+            const float a = __double2float_rn(__dmul_rn((double)width, __dsub_rn((double)nv, 0.5)));
+            y[base + i] = (int16_t)vs_round2int(__dadd_rn((double)y[base + i], (double)a));
+        }
+    }
+}
+
+cudaError_t vs_launch_vnoise(int16_t *pcm, const VsNoiseRow *rows, uint32_t n_rows, cudaStream_t s)
+{
+    vs_vnoise_kernel<<<(n_rows + VS_NT - 1) / VS_NT, VS_NT, 0, s>>>(pcm, rows, n_rows);
+    return cudaGetLastError();
+}
+
 /* ------------------------------------------------------------------------------------------------
  * FP64 pipe peak: 8 independent DFMA chains per thread, every SM full.  Used by bench.py to put a
  * measured denominator next to the HBM-write roofline.
