@@ -104,7 +104,7 @@ __device__ void vs_rng_seed(VsRng &g, uint32_t seed)
     for (int i = 0; i < 310; i++) (void)vs_rng_next<STRIDE>(g);
 }
 
-/* store / load the state in canonical rotation (oldest word first => f = 3 after loading) */
+/* store the state rotated so that a reader may assume f = 3: words 0..2 are the newest, word 3 the oldest */
 template <int STRIDE = VS_NT>
 __device__ void vs_rng_save(const VsRng &g, uint32_t *dst)
 {
@@ -114,12 +114,6 @@ __device__ void vs_rng_save(const VsRng &g, uint32_t *dst)
         j = (j == VS_RNG_DEG - 1) ? 0 : j + 1;
     }
 }
-__device__ void vs_rng_load(VsRng &g, const uint32_t *src)
-{
-    for (int k = 0; k < VS_RNG_DEG; k++) g.r[k * VS_NT] = src[k];
-    g.f = 3;
-}
-
 /* ------------------------------------------------------------------------------------------------
  * pulse samples (flowgen_shimmer.c:319, :328) and the noise sample (:387, :394, :591-600)
  *   rising : ceil((A*0.5)*(1-c)) == ceil(A*h) with h = 0.5*(1-c) tabulated (scaling by 0.5 is exact)
@@ -320,7 +314,9 @@ struct __align__(16) VsLane {
     int32_t nstart, lo, hi, blk0;
     int32_t T2, DCi, DCs, noise;
     uint32_t tab_cap;        /* entries of the row's period table: indices are checked against it */
-    uint32_t pad[3];
+    uint32_t chunk;          /* chunk id (noise: where the row's RNG snapshot lives)              */
+    uint32_t q0;             /* the chunk's first period: its perturbation draws are already consumed */
+    uint32_t pad;
 };
 
 struct VsEnt {               /* a period-table entry in registers */
@@ -397,34 +393,56 @@ struct __align__(16) VsSeg {
 #define VS_SMEM_TILES(NTILE) (VS_NP * (NTILE) * VS_TILE_I16 * 2)
 #define VS_SMEM_LANES (VS_NP * 32 * (int)sizeof(VsLane))
 #define VS_SMEM_SEGS  (VS_NP * 32 * VS_MAXSEG * (int)sizeof(VsSeg))
-#define VS_SMEM_NSEG  (VS_NP * 32 * 4 + VS_NP * 32 * VS_MAXSEG * 4)   /* per-row segment counts + T3|T4 per segment (noise) */
+#define VS_SEGX       3                                                /* noise words per segment: T3|T4, NoiseDistWidth, draws to skip */
+#define VS_SMEM_NSEG  (VS_NP * 32 * 4 + VS_NP * 32 * VS_MAXSEG * VS_SEGX * 4)   /* per-row segment counts + noise words */
 #define VS_ITEMS_BYTES (((32 * VS_MAXSEG * 4 + 4) * 2 + 15) & ~15)      /* work-item list of one producer warp */
 #define VS_SMEM_ITEMS(NPROD) (VS_NP * (NPROD) * VS_ITEMS_BYTES)
 #define VS_SMEM_BASE(NTILE) (VS_SMEM_TILES(NTILE) + VS_SMEM_LANES + VS_SMEM_SEGS + VS_SMEM_NSEG + VS_SMEM_ITEMS((NTILE) == 2 ? VS_PW : 1))
-/* noise: RNG states [31][VS_NT] words + the window's noise samples [NP][32][VS_WIN] int16 */
-#define VS_SMEM_NOISE (VS_RNG_DEG * VS_NT * 4 + VS_NP * 32 * VS_WIN * 2)
+/* noise: one RNG state per row, [NP][32 rows][32 words], oldest word first, and a
+ * scratch of random() values per producer warp */
+#define VS_DRAW_SCRATCH 224                /* >= 7 rounds of 31 values >= VS_WIN */
+#define VS_SMEM_NOISE (VS_NP * 32 * 32 * 4 + VS_NP * VS_PW * VS_DRAW_SCRATCH * 4)
 
 __device__ __forceinline__ void vs_named_barrier(int id, int count)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-/* ---- noise: lane = row; the row's noise samples w (flowgen_shimmer.c:387,398) for window w -------- */
-__device__ __forceinline__ void vs_draw_window(const VsLane &me, int w, VsRng &g, VsEnt &re, uint32_t &rq, int16_t *dr)
+/* ---- noise: the warp steps ONE row's random() 31 values at a time ------------------------------------
+ * glibc TYPE_3 is r[n] = r[n-31] + r[n-3] (mod 2^32), output r[n] >> 1.  With lane l < 31 holding
+ * st[l] = r[n-31+l], the next 31 words are prefix sums along the three stride-3 chains:
+ *     new[l] = st[l] + (l < 3 ? st[28+l] : new[l-3])
+ * i.e. an inclusive scan with shuffle distances 3, 6, 12, 24 (chains are at most 11 long). */
+__device__ __forceinline__ uint32_t vs_rng_round(uint32_t st, int lane)
 {
-    const int wb = me.blk0 + w * VS_WIN;
-    if (!me.noise || wb >= me.hi) return;
-    const int mlo = max(wb, me.nstart), mhi = min(wb + VS_WIN, me.hi);
-    for (int m = mlo; m < mhi; m++) {
-        int i = m - re.start;
-        while (i >= re.T) {                                   /* next period: its perturbation and K */
-            if (rq + 1 >= me.tab_cap) return;                 /* never walk past the row's table      */
-            re = vs_load_entry(me.tab + (++rq));              /* draws come first (:283,:298,:325)   */
-            for (int k = 0; k < re.npert; k++) (void)vs_rng_next(g);
-            i = m - re.start;
-        }
-        if (i < re.T4 || i >= re.T3) dr[m - wb] = (int16_t)vs_noise_w(vs_rng_next(g), re.ndw);
+    const uint32_t wrap = __shfl_sync(VS_FULL, st, (lane + 28) & 31);
+    uint32_t v = st + (lane < 3 ? wrap : 0u), u;
+    u = __shfl_up_sync(VS_FULL, v, 3);  if (lane >= 3)  v += u;
+    u = __shfl_up_sync(VS_FULL, v, 6);  if (lane >= 6)  v += u;
+    u = __shfl_up_sync(VS_FULL, v, 12); if (lane >= 12) v += u;
+    u = __shfl_up_sync(VS_FULL, v, 24); if (lane >= 24) v += u;
+    return v;
+}
+
+/* advance the row's generator by m values; they go to out[0..m) when out is not NULL.  Returns the new
+ * state (lanes 0..30).  m is warp-uniform. */
+__device__ __forceinline__ uint32_t vs_rng_gen(uint32_t st, int m, int lane, int32_t *out)
+{
+    int done = 0;
+    for (; m - done >= VS_RNG_DEG; done += VS_RNG_DEG) {
+        st = vs_rng_round(st, lane);
+        if (out && lane < VS_RNG_DEG) out[done + lane] = (int32_t)(st >> 1);
     }
+    const int u = m - done;
+    if (u > 0) {                                     /* part of a round: the state window slides by u words */
+        const uint32_t nx = vs_rng_round(st, lane);
+        if (out && lane < u) out[done + lane] = (int32_t)(nx >> 1);
+        const int src = lane + u;
+        const uint32_t keep = __shfl_sync(VS_FULL, st, src & 31);
+        const uint32_t fresh = __shfl_sync(VS_FULL, nx, (src - VS_RNG_DEG) & 31);
+        st = src < VS_RNG_DEG ? keep : fresh;
+    }
+    return st;
 }
 
 /* ---- G: generate window w of the rows {row0, row0+step, ...} of a tile --------------------------------
@@ -439,11 +457,11 @@ __device__ __forceinline__ void vs_draw_window(const VsLane &me, int w, VsRng &g
 template <int MODE, bool NOISE>
 __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, VsSeg *segs, int *nsegs, uint16_t *items,
                                             int w, int lane, int row0, int step, const VsLane &mine, uint32_t &q,
-                                            const int16_t *noisebuf)
+                                            uint32_t *rngrow, int32_t *scratch)
 {
     const int myrow = row0 + lane * step;
     const bool have_row = myrow < 32;
-    uint32_t *t34 = reinterpret_cast<uint32_t *>(nsegs + 32);      /* [32][VS_MAXSEG] T3|T4 per queued segment (noise) */
+    uint32_t *segx = reinterpret_cast<uint32_t *>(nsegs + 32);     /* [32][VS_MAXSEG][VS_SEGX] noise words per queued segment */
 
     if (MODE == VS_MODE_FILTER) {
         for (int j = row0; j < 32; j += step) {
@@ -504,7 +522,15 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
                         sg.out = tile + myrow * VS_TS + (e.start - wb_m);
                         sg.a0 = a0; sg.a1 = a1; sg.T2 = mine.T2; sg.DCi = mine.DCi;
                         my[n] = sg;
-                        if (NOISE) t34[myrow * VS_MAXSEG + n] = (uint32_t)e.T3 | ((uint32_t)e.T4 << 16);
+                        if (NOISE) {
+                            uint32_t *x = segx + (myrow * VS_MAXSEG + n) * VS_SEGX;
+                            x[0] = (uint32_t)e.T3 | ((uint32_t)e.T4 << 16);
+                            x[1] = (uint32_t)e.ndw;
+                            /* a period that begins in this window draws its perturbations and K before
+                             * its first noise sample (:283,:298,:325); the chunk's first period has
+                             * them behind it already (the snapshot is taken after its K draw) */
+                            x[2] = (a0 == 0 && q != mine.q0) ? (uint32_t)e.npert : 0u;
+                        }
                         const int gcnt = nopen > 0 ? (nopen + VS_ITEM_SAMPLES - 1) / VS_ITEM_SAMPLES : 0;
                         grp_counts |= (uint32_t)gcnt << (4 * n);
                         ngrp += gcnt;
@@ -564,17 +590,28 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
             for (int j = row0; j < 32; j += step) {
                 if (!lanes[j].noise) continue;
                 const int cnt = nsegs[j];
-                int16_t *trow = tile + j * VS_TS;
-                const int16_t *nrow = noisebuf + j * VS_WIN;
+                if (cnt == 0) continue;
+                uint32_t st = rngrow[j * 32 + lane];
                 for (int sidx = 0; sidx < cnt; sidx++) {
                     const VsSeg sg = segs[j * VS_MAXSEG + sidx];
-                    const uint32_t tt = t34[j * VS_MAXSEG + sidx];
-                    const int T3 = (int)(tt & 0xffffu), T4 = (int)(tt >> 16);
-                    const int rel = (int)(sg.out - trow);
-                    for (int i = sg.a0 + lane; i < sg.a1; i += 32)
-                        if (i < T4 || i >= T3)
-                            trow[rel + i] = (int16_t)vs_add_clip(trow[rel + i], nrow[rel + i]);
+                    const uint32_t *x = segx + (j * VS_MAXSEG + sidx) * VS_SEGX;
+                    const int T3 = (int)(x[0] & 0xffffu), T4 = (int)(x[0] >> 16);
+                    const int ndw = (int)x[1], skip = (int)x[2];
+                    if (skip) st = vs_rng_gen(st, skip, lane, nullptr);
+                    /* the period's noise samples inside this window, in draw order: [.., T4) then [T3, ..) */
+                    const int n1hi = min(sg.a1, T4), n2lo = max(sg.a0, T3);
+                    const int c1 = max(0, n1hi - sg.a0), c2 = max(0, sg.a1 - n2lo);
+                    if (c1 + c2 > 0) {
+                        st = vs_rng_gen(st, c1 + c2, lane, scratch);
+                        __syncwarp();
+                        for (int i = sg.a0 + lane; i < n1hi; i += 32)
+                            sg.out[i] = (int16_t)vs_add_clip(sg.out[i], vs_noise_w(scratch[i - sg.a0], ndw));
+                        for (int i = n2lo + lane; i < sg.a1; i += 32)
+                            sg.out[i] = (int16_t)vs_add_clip(sg.out[i], vs_noise_w(scratch[c1 + i - n2lo], ndw));
+                        __syncwarp();
+                    }
                 }
+                rngrow[j * 32 + lane] = st;
             }
         }
         __syncwarp();
@@ -662,7 +699,7 @@ vs_render_kernel(const VsRenderArgs a)
     int *s_nseg = reinterpret_cast<int *>(s_raw + VS_SMEM_TILES(NTILE) + VS_SMEM_LANES + VS_SMEM_SEGS);
     unsigned char *s_items = s_raw + VS_SMEM_TILES(NTILE) + VS_SMEM_LANES + VS_SMEM_SEGS + VS_SMEM_NSEG;
     uint32_t *s_rng = reinterpret_cast<uint32_t *>(s_raw + VS_SMEM_BASE(NTILE));
-    int16_t *s_noise = reinterpret_cast<int16_t *>(s_raw + VS_SMEM_BASE(NTILE) + VS_RNG_DEG * VS_NT * 4);
+    int32_t *s_scratch = reinterpret_cast<int32_t *>(s_raw + VS_SMEM_BASE(NTILE) + VS_NP * 32 * 32 * 4);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int pair = warp % VS_NP;                       /* warps 0..NP-1 consume, NP.. produce */
@@ -672,8 +709,9 @@ vs_render_kernel(const VsRenderArgs a)
     int16_t *tile0 = s_tiles + pair * NTILE * VS_TILE_I16;
     VsLane *lanes = s_lanes + pair * 32;
     VsSeg *segs = s_segs + pair * 32 * VS_MAXSEG;
-    int *nsegs = s_nseg + pair * (32 + 32 * VS_MAXSEG);
-    int16_t *noisebuf = s_noise + pair * 32 * VS_WIN;
+    int *nsegs = s_nseg + pair * (32 + 32 * VS_MAXSEG * VS_SEGX);
+    uint32_t *rngrow = DRAWS ? s_rng + pair * 32 * 32 : nullptr;
+    int32_t *scratch = DRAWS ? s_scratch + (pair * VS_PW + (prod > 0 ? prod : 0)) * VS_DRAW_SCRATCH : nullptr;
     uint16_t *items = reinterpret_cast<uint16_t *>(s_items + (pair * (PAIRED ? VS_PW : 1) + (prod > 0 ? prod : 0)) * VS_ITEMS_BYTES);
     const int group_threads = (1 + VS_PW) * 32;
 
@@ -690,7 +728,7 @@ vs_render_kernel(const VsRenderArgs a)
     VsLane me;
     me.tab = nullptr; me.ct = nullptr; me.orow = nullptr; me.fin = nullptr;
     me.nstart = 0; me.lo = 0; me.hi = 0; me.blk0 = 0; me.T2 = 0; me.DCi = 0; me.DCs = 0; me.noise = 0; me.tab_cap = 0;
-    me.pad[0] = me.pad[1] = me.pad[2] = 0;
+    me.chunk = chunk_id; me.q0 = 0; me.pad = 0;
     if (active) {
         const VsChunk ck = a.chunks[chunk_id];
         const VsStream st = a.streams[ck.stream];
@@ -708,6 +746,7 @@ vs_render_kernel(const VsRenderArgs a)
             me.noise = (st.flags & VS_F_NOISE) ? 1 : 0;
             me.tab_cap = st.tab_cap;
             q = ck.first_period;
+            me.q0 = q;
             if (q >= st.tab_cap) {                    /* the plan kernel did not reach this chunk: refuse to walk garbage */
                 atomicExch(a.status, VS_ECUDA);
                 q = 0; me.hi = 0; me.lo = 0;
@@ -725,25 +764,21 @@ vs_render_kernel(const VsRenderArgs a)
     for (int o = 16; o > 0; o >>= 1) nwin = max(nwin, __shfl_xor_sync(VS_FULL, nwin, o));
     if (!consumer && myrow < 32) lanes[myrow] = me;          /* producers publish the row descriptors */
 
-    /* noise: the book-keeping lane owns its row's RNG, restored from the plan kernel's snapshot */
-    VsRng g;
-    g.r = s_rng + (DRAWS ? pair * 32 + (myrow & 31) : 0);
-    g.f = 3;
-    VsEnt re;
-    re.start = 0; re.T = 0x7fffffff; re.T3 = 0; re.T4 = 0; re.npert = 0; re.ndw = 0; re.Ad = re.Kd = 0.0;
-    uint32_t rq = q;
-    if (DRAWS && !consumer && active && me.noise) {
-        vs_rng_load(g, a.rng_snap + (size_t)chunk_id * 32);
-        re = vs_load_entry(me.tab + rq);
+    /* noise: the rows' RNG states (oldest word in lane 0), restored from the plan kernel's snapshots */
+    if (DRAWS && !consumer) {
+        __syncwarp();
+        for (int j = prod > 0 ? prod : 0; j < 32; j += step)
+            if (lanes[j].noise && lanes[j].chunk != VS_NO_CHUNK)
+                rngrow[j * 32 + lane] =                  /* snapshot has f = 3: word 3 is the oldest, words 0..2 the newest */
+                    lane < VS_RNG_DEG ? __ldg(a.rng_snap + (size_t)lanes[j].chunk * 32 + (lane + 3) % VS_RNG_DEG) : 0u;
+        __syncwarp();
     }
-    int16_t *mynoise = noisebuf + (myrow & 31) * VS_WIN;
 
     if (!PAIRED) {
         /* ======== flow mode: one warp, G then W ======== */
         __syncwarp();
         for (int w = 0; w < nwin; w++) {
-            if (DRAWS) { if (active) vs_draw_window(me, w, g, re, rq, mynoise); __syncwarp(); }
-            vs_gen_tile<MODE, NOISE>(tile0, lanes, segs, nsegs, items, w, lane, 0, 1, me, q, noisebuf);
+            vs_gen_tile<MODE, NOISE>(tile0, lanes, segs, nsegs, items, w, lane, 0, 1, me, q, rngrow, scratch);
             __syncwarp();
             for (int j = 0; j < 32; j++) vs_write_row(tile0 + j * VS_TS, lanes[j], w, lane);
             __syncwarp();
@@ -774,18 +809,14 @@ vs_render_kernel(const VsRenderArgs a)
             vs_named_barrier(1 + pair, group_threads);
         }
     } else {
-        if (DRAWS && active) vs_draw_window(me, 0, g, re, rq, mynoise);
-        __syncwarp();
-        vs_gen_tile<MODE, NOISE>(tile0, lanes, segs, nsegs, items, 0, lane, prod, step, me, q, noisebuf);
+        vs_gen_tile<MODE, NOISE>(tile0, lanes, segs, nsegs, items, 0, lane, prod, step, me, q, rngrow, scratch);
         vs_named_barrier(1 + pair, group_threads);           /* window 0 generated */
         for (int w = 0; w < nwin; w++) {
             int16_t *other = tile0 + ((w + 1) & 1) * VS_TILE_I16;
             if (w > 0)
                 for (int j = prod; j < 32; j += step) vs_write_row(other + j * VS_TS, lanes[j], w - 1, lane);
             if (w + 1 < nwin) {
-                if (DRAWS && active) vs_draw_window(me, w + 1, g, re, rq, mynoise);
-                __syncwarp();
-                vs_gen_tile<MODE, NOISE>(other, lanes, segs, nsegs, items, w + 1, lane, prod, step, me, q, noisebuf);
+                vs_gen_tile<MODE, NOISE>(other, lanes, segs, nsegs, items, w + 1, lane, prod, step, me, q, rngrow, scratch);
             }
             vs_named_barrier(1 + pair, group_threads);
         }
