@@ -123,6 +123,8 @@ typedef struct vs_timing {
 #define VS_OPT_ASYNC_HOST      7  /* 1: calls with PINNED host buffers also return after enqueueing; the
                                      PCM of call k crosses PCIe while call k+1 renders (two device
                                      scratch buffers alternate).  vs_sync() before reading.  (0)          */
+#define VS_OPT_PLAN_WARPS      8  /* period-table kernel: 1 = one warp per stream, 0 = one thread per
+                                     stream, -1 = auto: warps for small batches and glottal noise (-1)    */
 
 /* ---- context -------------------------------------------------------------------------------- */
 int         vs_ctx_create(vs_ctx **out, const int *devices, int n_devices, uint32_t flags);

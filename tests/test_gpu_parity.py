@@ -64,6 +64,38 @@ def test_flowgen_matches_reference_fixtures(ctx, vs, golden, oracle):
             assert np.array_equal(a, b, equal_nan=True), (c["name"], k, np.flatnonzero(a != b)[:5])
 
 
+@pytest.mark.parametrize("plan_warps", [0, 1])
+def test_both_plan_kernels_match_reference_fixtures(ctx, vs, golden, plan_warps):
+    """the period table comes from one thread per stream or one warp per stream (VS_OPT_PLAN_WARPS): both must
+    reproduce the reference PCM, unchunked and with chunks that start from RNG snapshots"""
+    cases, p = _golden_flow_params(golden, vs)
+    ctx.set_option(vs.OPT_PLAN_WARPS, plan_warps)
+    try:
+        for L in (0, 1000):
+            ctx.set_option(vs.OPT_CHUNK_SAMPLES, L)
+            out, offs, ns = ctx.flowgen_batch(p)
+            for i, c in enumerate(cases):
+                pcm = out[int(offs[i]): int(offs[i]) + int(ns[i])]
+                assert sha(pcm) == c["sha256"], (c["name"], c["seed"], L)
+    finally:
+        ctx.set_option(vs.OPT_CHUNK_SAMPLES, 0)
+        ctx.set_option(vs.OPT_PLAN_WARPS, -1)
+
+
+def test_plan_kernels_agree_on_random_batches(ctx, vs):
+    """512 random voices of cfg2 and 512 of cfg3 (glottal noise): identical flow from both plan kernels"""
+    from voice_synth_b200 import workloads
+    for make in (workloads.cfg2, workloads.cfg3):
+        p, _ = make(n=512)
+        outs = []
+        for w in (0, 1):
+            ctx.set_option(vs.OPT_PLAN_WARPS, w)
+            out, _, _ = ctx.flowgen_batch(p)
+            outs.append(out.copy())
+        ctx.set_option(vs.OPT_PLAN_WARPS, -1)
+        assert np.array_equal(outs[0], outs[1]), make.__name__
+
+
 def test_flowgen_chunked_equals_unchunked(ctx, vs, golden):
     cases, p = _golden_flow_params(golden, vs)
     ref, offs, ns = ctx.flowgen_batch(p)

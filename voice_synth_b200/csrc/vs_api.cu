@@ -28,7 +28,7 @@
 #include "vs_presets.h"
 
 enum { VS_MODE_FLOW = 0, VS_MODE_SYNTH = 1, VS_MODE_FILTER = 2 };
-cudaError_t vs_launch_plan(const VsPlanArgs &a, bool want_log, cudaStream_t s);
+cudaError_t vs_launch_plan(const VsPlanArgs &a, bool want_log, bool warp_per_stream, cudaStream_t s);
 cudaError_t vs_launch_render(const VsRenderArgs &a, int mode, bool noise, bool exact, cudaStream_t s);
 cudaError_t vs_launch_fp64_peak(double *scratch, int blocks, int iters, cudaStream_t s);
 cudaError_t vs_launch_vnoise(int16_t *pcm, const VsNoiseRow *rows, uint32_t n_rows, cudaStream_t s);
@@ -87,6 +87,7 @@ struct vs_ctx {
     std::vector<Slot> slots;
     double opt_chunk = 0;        /* 0 auto, <0 never, >0 fixed */
     double opt_tol = 1e-13;
+    int opt_plan_warps = -1;     /* -1 auto, 0 one thread per stream, 1 one warp per stream */
     int opt_exact = 0;
     int opt_slab = 0;
     double opt_warps = 2.0;
@@ -812,7 +813,11 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 pa.log = want_log ? sl.log.p : nullptr;
                 pa.status = (int32_t *)sl.status[cp].p;
                 pa.need_pulse = want_log;
-                CU(vs_launch_plan(pa, want_log, sl.plan));
+                /* one warp per stream while the batch is too small to fill the GPU with one thread per stream;
+                 * with glottal noise (hundreds of serial pulse samples and draws per period and thread) that
+                 * holds for much larger batches */
+                const bool plan_warps = ctx->opt_plan_warps < 0 ? pa.n_streams <= (any_noise ? VS_PLAN_WARP_MAX_NOISE : VS_PLAN_WARP_MAX) : ctx->opt_plan_warps != 0;
+                CU(vs_launch_plan(pa, want_log, plan_warps, sl.plan));
                 ctx->timing.launches++;
             }
         }
@@ -1067,6 +1072,7 @@ int vs_ctx_set_option(vs_ctx *ctx, int option, double value)
     case VS_OPT_SLAB_STREAMS: ctx->opt_slab = value > 0 ? (int)value : 0; return VS_OK;
     case VS_OPT_TARGET_WARPS: if (!(value > 0)) return VS_EINVAL; ctx->opt_warps = value; return VS_OK;
     case VS_OPT_ASYNC_HOST: ctx->opt_async_host = value != 0.0; return VS_OK;
+    case VS_OPT_PLAN_WARPS: ctx->opt_plan_warps = value < 0 ? -1 : (value != 0.0); return VS_OK;
     default: return VS_EINVAL;
     }
 }

@@ -300,6 +300,358 @@ __global__ void __launch_bounds__(VS_PLAN_NT, 1) vs_plan_kernel(const VsPlanArgs
     a.n_periods[s] = np;
 }
 
+/* ---- noise: the warp steps ONE row's random() 31 values at a time ------------------------------------
+ * glibc TYPE_3 is r[n] = r[n-31] + r[n-3] (mod 2^32), output r[n] >> 1.  With lane l < 31 holding
+ * st[l] = r[n-31+l], the next 31 words are prefix sums along the three stride-3 chains:
+ *     new[l] = st[l] + (l < 3 ? st[28+l] : new[l-3])
+ * i.e. an inclusive scan with shuffle distances 3, 6, 12, 24 (chains are at most 11 long). */
+__device__ __forceinline__ uint32_t vs_rng_round(uint32_t st, int lane)
+{
+    const uint32_t wrap = __shfl_sync(VS_FULL, st, (lane + 28) & 31);
+    uint32_t v = st + (lane < 3 ? wrap : 0u), u;
+    u = __shfl_up_sync(VS_FULL, v, 3);  if (lane >= 3)  v += u;
+    u = __shfl_up_sync(VS_FULL, v, 6);  if (lane >= 6)  v += u;
+    u = __shfl_up_sync(VS_FULL, v, 12); if (lane >= 12) v += u;
+    u = __shfl_up_sync(VS_FULL, v, 24); if (lane >= 24) v += u;
+    return v;
+}
+
+/* advance the row's generator by m values; they go to out[0..m) when out is not NULL.  Returns the new
+ * state (lanes 0..30).  m is warp-uniform. */
+__device__ __forceinline__ uint32_t vs_rng_gen(uint32_t st, int m, int lane, int32_t *out)
+{
+    int done = 0;
+    for (; m - done >= VS_RNG_DEG; done += VS_RNG_DEG) {
+        st = vs_rng_round(st, lane);
+        if (out && lane < VS_RNG_DEG) out[done + lane] = (int32_t)(st >> 1);
+    }
+    const int u = m - done;
+    if (u > 0) {                                     /* part of a round: the state window slides by u words */
+        const uint32_t nx = vs_rng_round(st, lane);
+        if (out && lane < u) out[done + lane] = (int32_t)(nx >> 1);
+        const int src = lane + u;
+        const uint32_t keep = __shfl_sync(VS_FULL, st, src & 31);
+        const uint32_t fresh = __shfl_sync(VS_FULL, nx, (src - VS_RNG_DEG) & 31);
+        st = src < VS_RNG_DEG ? keep : fresh;
+    }
+    return st;
+}
+
+/* ================================================================================================
+ * PLAN, one WARP per stream: for small batches (a single ten-minute stream is 71 k sequential periods)
+ * and for streams with glottal noise, where one thread per stream leaves the GPU idle or crawls through
+ * hundreds of serial pulse samples and noise draws per period.
+ *   - random(): 31 values per round by the whole warp (vs_rng_round);
+ *   - every value's three possible meanings (jitter draw, shimmer draw, closure-speed draw; they do not
+ *     depend on the walk's state) are worked out lane-parallel, one value per lane, incl. the two
+ *     divisions whose numerator is state-free and a refined reciprocal for the one that is not;
+ *   - the walk itself (flowgen_shimmer.c:276-325) runs warp-uniform, reading those values back by
+ *     broadcast; its remaining division is the reciprocal-multiply sequence with an exactness check and
+ *     an IEEE division when the check is inconclusive;
+ *   - with noise: the open phase is evaluated 32 samples per step, the float power sum then runs in
+ *     index order over the 32 squares (the sum is not associative), and the period's noise draws are
+ *     stepped over with vs_rng_gen.
+ * Same tables, chunk marks and RNG snapshots as vs_plan_kernel<false>.
+ * ============================================================================================== */
+#define VS_PLANW_NT 128
+
+/* n/d given y ~ 1/d; sets doubt unless the result is provably the correctly rounded quotient */
+__device__ __forceinline__ double vs_div_checked_y(double n, double d, double y, bool &doubt)
+{
+    const double q0 = __dmul_rn(n, y);
+    const double q = __fma_rn(__fma_rn(-q0, d, n), y, q0);
+    const double rem = __fma_rn(-q, d, n);
+    const int e = (__double2hiint(q) >> 20) & 0x7ff;                /* ulp(q)/2 = 2^(e-53-1023) */
+    const double half_ulp = __hiloint2double((e - 53) << 20, 0);
+    const bool sure = (e > 60 && e < 0x7fe) && (fabs(rem) < __dmul_rn(half_ulp, fabs(d)));
+    doubt = !sure && !(q == 0.0 && rem == 0.0);
+    return q;
+}
+__device__ __forceinline__ double vs_recip_refined(double d)
+{
+    double y = (double)__frcp_rn((float)d);
+    y = __fma_rn(y, __fma_rn(-d, y, 1.0), y);
+    y = __fma_rn(y, __fma_rn(-d, y, 1.0), y);
+    y = __fma_rn(y, __fma_rn(-d, y, 1.0), y);
+    return y;
+}
+
+__global__ void __launch_bounds__(VS_PLANW_NT) vs_plan_warp_kernel(const VsPlanArgs a)
+{
+    /* per random() value, in a ring of 64 slots (two rounds of 31 are outstanding at most):
+     * 2+J, 2-J, 1/(2-J), 2P*J/(2-J); the same four for S; Knew */
+    __shared__ double s_itp[VS_PLANW_NT / 32][8][64];
+    __shared__ float s_kn[VS_PLANW_NT / 32][64];
+    __shared__ __align__(16) float s_sq[VS_PLANW_NT / 32][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t s = blockIdx.x * (VS_PLANW_NT / 32) + wib;
+    if (s >= a.n_streams) return;
+    const VsStream st = a.streams[s];
+    double (*itp)[64] = s_itp[wib];
+    float *kn = s_kn[wib];
+    float *sqb = s_sq[wib];
+
+    const bool do_jit = (st.flags & VS_F_JITTER) && st.jitter != 0.0f;    /* :248 */
+    const bool do_shm = (st.flags & VS_F_SHIMMER) && st.shimmer != 0.0f;  /* :295 */
+    const bool noise = (st.flags & VS_F_NOISE) != 0;                      /* :373 */
+    const int P = st.P, T2 = st.T2;
+    const float Pf = (float)P, ampf = (float)st.amp;
+    const float t_hi = __fmul_rn(1.2f, Pf), t_lo = __fmul_rn(0.8f, Pf);
+    const float a_hi = __fmul_rn(1.8f, ampf), a_lo = __fmul_rn(0.2f, ampf);
+    const double jit = (double)st.jitter, shm = (double)st.shimmer;
+    const double jit2 = __dmul_rn(2.0, jit), shm2 = __dmul_rn(2.0, shm);
+    const double P2 = __dmul_rn(2.0, (double)P), amp2 = __dmul_rn(2.0, (double)st.amp);
+    const double Kbase = (double)st.K, kv2 = (double)__fmul_rn(2.0f, st.Kvar);
+    const double *ht = a.costab + st.cos_off;
+    const double *ct = ht + T2;
+    const int DCi = (int)ceilf(st.DC);
+    const int DCs = st.DCs;
+
+    /* srandom (flowgen_shimmer.c:241): every lane runs the 30 Schrage steps, lane l keeps the word that is
+     * l-th oldest once f = 3, i.e. word (l+3) mod 31; then the 310 discarded values = 10 rounds */
+    uint32_t rs;
+    {
+        int32_t w = (int32_t)(st.seed ? st.seed : 1u);
+        const int want = (lane + 3) % VS_RNG_DEG;
+        rs = (uint32_t)w;
+        for (int i = 1; i < VS_RNG_DEG; i++) {
+            const int32_t hi = w / 127773, lo = w % 127773;
+            w = 16807 * lo - 2836 * hi;
+            if (w < 0) w += 2147483647;
+            if (i == want) rs = (uint32_t)w;
+        }
+        for (int k = 0; k < 10; k++) rs = vs_rng_round(rs, lane);
+    }
+
+    /* Value source.  Values are numbered from the last reset; value i lives in ring slot i & 63.
+     * rs = generator state before round A; nxa = round A = values [base, base+31); nxb = round B =
+     * values [base+31, base+62) once have_b; pos = next value to use. */
+    uint32_t nxa = 0, nxb = 0;
+    int base = 0, pos = 0;
+    bool have_b = false;
+    auto interpret = [&](uint32_t words, int first) {     /* lane-parallel: what each value means as J, S, K draw */
+        __syncwarp();
+        if (lane < VS_RNG_DEG) {
+            const int32_t r = (int32_t)(words >> 1);
+            const int slot = (first + lane) & 63;
+            if (do_jit) {                                                  /* :277-281 */
+                double t = vs_div_const((double)r, VS_RM4, VS_INV_RM4);
+                t = __dmul_rn(__dmul_rn(t, 40000.0), jit);
+                const double J = (double)__double2float_rn(__dsub_rn(t, jit2));
+                const double den = __dsub_rn(2.0, J), y = vs_recip_refined(den), num = __dmul_rn(P2, J);
+                bool doubt;
+                double q = vs_div_checked_y(num, den, y, doubt);
+                if (doubt) q = __ddiv_rn(num, den);
+                itp[0][slot] = __dadd_rn(2.0, J);
+                itp[1][slot] = den;
+                itp[2][slot] = y;
+                itp[3][slot] = q;
+            }
+            if (do_shm) {                                                  /* :297-301 */
+                const float eps = __fmul_rn((float)r, 4.656612873077393e-10f);
+                const double S = (double)__double2float_rn(__dsub_rn(__dmul_rn(__dmul_rn((double)eps, 4.0), shm), shm2));
+                const double den = __dsub_rn(2.0, S), y = vs_recip_refined(den), num = __dmul_rn(amp2, S);
+                bool doubt;
+                double q = vs_div_checked_y(num, den, y, doubt);
+                if (doubt) q = __ddiv_rn(num, den);
+                itp[4][slot] = __dadd_rn(2.0, S);
+                itp[5][slot] = den;
+                itp[6][slot] = y;
+                itp[7][slot] = q;
+            }
+            const double kq = __dsub_rn(vs_div_const((double)r, VS_RAND_MAX_D, VS_INV_RM), 0.5);   /* :325 */
+            kn[slot] = __double2float_rn(__dmul_rn(Kbase, __dadd_rn(1.0, __dmul_rn(kv2, kq))));
+        }
+        __syncwarp();
+    };
+    auto restart = [&](uint32_t state) {                  /* value numbering starts again at this generator state */
+        rs = state;
+        nxa = vs_rng_round(rs, lane);
+        base = 0; pos = 0; have_b = false;
+        interpret(nxa, 0);
+    };
+    auto make_b = [&]() {
+        nxb = vs_rng_round(nxa, lane);
+        interpret(nxb, base + VS_RNG_DEG);
+        have_b = true;
+    };
+    auto refill = [&](bool ahead) {                       /* afterwards pos < base+31, and round B exists if `ahead` */
+        while (pos >= base + VS_RNG_DEG) {
+            if (!have_b) make_b();
+            rs = nxa; nxa = nxb; base += VS_RNG_DEG; have_b = false;
+        }
+        if (ahead && !have_b) make_b();
+    };
+    auto slide = [&](uint32_t before, uint32_t words, int u) -> uint32_t {   /* state after u (0..31) values of a round */
+        const int src = lane + u;
+        const uint32_t keep = __shfl_sync(VS_FULL, before, src & 31);
+        const uint32_t fr = __shfl_sync(VS_FULL, words, (src - VS_RNG_DEG) & 31);
+        return src < VS_RNG_DEG ? keep : fr;
+    };
+    auto state_now = [&]() -> uint32_t {                  /* lanes 0..30, oldest word first */
+        const int off = pos - base;                       /* 0..62 */
+        return off <= VS_RNG_DEG ? slide(rs, nxa, off) : slide(nxa, nxb, off - VS_RNG_DEG);
+    };
+    restart(rs);
+
+    int T = P, T4 = 0, ndw = 0;
+    float dper = 0.0f, dsh = 0.0f;
+    uint32_t count = 0, np = 0, next_c = 0;
+    VsPeriod *tab = a.table + st.tab_off;
+    VsChunk *chunks = a.chunks + st.chunk0;
+    uint32_t next_target = st.n_chunks ? chunks[0].gen_target : 0xffffffffu;
+    int guard = 0;
+    const bool both = do_jit && do_shm;
+
+    do {
+        uint32_t nd = 0;
+        float A = ampf, Knew = 0.0f;
+        bool committed = false;
+        /* without noise the values of consecutive periods are consecutive: keep a round in reserve so that
+         * the common case below never meets a round boundary */
+        refill(!noise);
+        /* Common case first: jitter and shimmer both on, every draw accepted at once.  The two random walks
+         * are independent recurrences, so their division chains run side by side; acceptance is tested on
+         * ceilf(P + dPer), the same integer as (short)ceil((double)..) when it is in range.  Anything else
+         * -- a rejected draw, an inconclusive division check -- takes the literal loops below from pos. */
+        if (both && (have_b || pos + 3 <= base + VS_RNG_DEG)) {
+            const int pj = pos & 63, ps = (pos + 1) & 63, pk = (pos + 2) & 63;
+            const double numj = __dmul_rn((double)dper, itp[0][pj]);
+            const double nums = __dmul_rn((double)dsh, itp[4][ps]);
+            bool dj, ds;
+            const double qj = vs_div_checked_y(numj, itp[1][pj], itp[2][pj], dj);
+            const double qs = vs_div_checked_y(nums, itp[5][ps], itp[6][ps], ds);
+            const float curJ = __double2float_rn(__dadd_rn(qj, itp[3][pj]));
+            const float curS = __double2float_rn(__dadd_rn(qs, itp[7][ps]));
+            const float Tf = ceilf(__fadd_rn(Pf, curJ));
+            const float An = __fadd_rn(ampf, curS);
+            const bool ok = !dj && !ds && !(Tf > t_hi || Tf < t_lo) && Tf >= 1.0f && Tf <= 32767.0f && !(An > a_hi || An < a_lo);
+            if (ok) {
+                dper = curJ; dsh = curS; T = (int)Tf; A = An;
+                Knew = kn[pk];
+                nd = 3u;
+                pos += 3;
+                committed = true;
+            }
+        }
+        if (!committed) {
+            if (do_jit) {                                                     /* :276-290 */
+                const double prev = (double)dper;
+                float cur;
+                for (;;) {
+                    refill(false);
+                    const int p = pos++ & 63; nd++;
+                    const double num = __dmul_rn(prev, itp[0][p]), den = itp[1][p];
+                    bool doubt;
+                    double q1 = vs_div_checked_y(num, den, itp[2][p], doubt);
+                    if (doubt) q1 = __ddiv_rn(num, den);
+                    cur = __double2float_rn(__dadd_rn(q1, itp[3][p]));
+                    T = (int)vs_d2s(ceil((double)__fadd_rn(Pf, cur)));
+                    if (++guard > (1 << 22)) { atomicExch(a.status, VS_ERANGE); return; }
+                    if (!((float)T > t_hi || (float)T < t_lo)) break;
+                }
+                dper = cur;
+            }
+            if (do_shm) {                                                     /* :296-306 */
+                const double prev = (double)dsh;
+                float cur;
+                for (;;) {
+                    refill(false);
+                    const int p = pos++ & 63; nd++;
+                    const double num = __dmul_rn(prev, itp[4][p]), den = itp[5][p];
+                    bool doubt;
+                    double q1 = vs_div_checked_y(num, den, itp[6][p], doubt);
+                    if (doubt) q1 = __ddiv_rn(num, den);
+                    cur = __double2float_rn(__dadd_rn(q1, itp[7][p]));
+                    A = __fadd_rn(ampf, cur);
+                    if (++guard > (1 << 22)) { atomicExch(a.status, VS_ERANGE); return; }
+                    if (!(A > a_hi || A < a_lo)) break;
+                }
+                dsh = cur;
+            }
+            if (T < 1 || T > 32767) { atomicExch(a.status, VS_ERANGE); return; }
+            refill(false);                                                    /* closure-speed draw (:325) */
+            Knew = kn[pos++ & 63]; nd++;
+        }
+
+        while (next_target < count + (uint32_t)T) {
+            if (lane == 0) chunks[next_c].first_period = np;
+            if (noise && a.rng_snap) {
+                const uint32_t now = state_now();
+                if (lane < VS_RNG_DEG) a.rng_snap[(size_t)(st.chunk0 + next_c) * 32 + (lane + 3) % VS_RNG_DEG] = now;
+            }
+            next_c++;
+            next_target = next_c < st.n_chunks ? chunks[next_c].gen_target : 0xffffffffu;
+        }
+
+        int T3 = 2 * T2;
+        if (noise) {
+            const double Ad = (double)A, Kd = (double)Knew;
+            float aux = 0.0f;
+            /* rising branch (:318-323): T4 = last index below DC; the power sum covers [T4, T2) whether T4
+             * moved in this period or is the stale one */
+            for (int b0 = 0; b0 < T2; b0 += 32) {
+                const int i = b0 + lane;
+                const bool valid = i < T2;
+                int x = valid ? vs_rising(Ad, __ldg(ht + i)) : 0;
+                const bool below = valid && x < DCi;
+                const uint32_t m = __ballot_sync(VS_FULL, below);
+                if (m) { T4 = b0 + 31 - __clz((int)m); aux = 0.0f; }
+                if (below) x = DCs;
+                sqb[lane] = (valid && i >= T4) ? __fmul_rn((float)x, (float)x) : 0.0f;
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const float4 v = reinterpret_cast<const float4 *>(sqb)[k];
+                    aux = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(aux, v.x), v.y), v.z), v.w);
+                }
+                __syncwarp();
+            }
+            /* falling branch (:327-332): stops at the first index below DC = T3 */
+            for (int b0 = T2; b0 < 2 * T2; b0 += 32) {
+                const int i = b0 + lane;
+                const bool valid = i < 2 * T2;
+                const int x = valid ? vs_falling(Ad, Kd, __ldg(ct + i - T2)) : 0;
+                const uint32_t m = __ballot_sync(VS_FULL, valid && x < DCi);
+                const int first = m ? __ffs((int)m) - 1 : 32;
+                sqb[lane] = (valid && lane < first) ? __fmul_rn((float)x, (float)x) : 0.0f;
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const float4 v = reinterpret_cast<const float4 *>(sqb)[k];
+                    aux = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(aux, v.x), v.y), v.z), v.w);
+                }
+                __syncwarp();
+                if (m) { T3 = b0 + first; break; }
+            }
+            /* :378-382 */
+            const float span = __fsub_rn((float)T3, (float)T4);
+            const float x_pow = __fdiv_rn(aux, span);
+            const float ax = __double2float_rn(__dadd_rn(1.0, (double)__fdiv_rn(span, (float)T)));
+            ndw = vs_d2i(sqrt((double)__fdiv_rn(__fmul_rn(__fmul_rn(12.0f, ax), x_pow), st.noise)));
+            const uint32_t n_noise = (uint32_t)(T4 + (T > T3 ? T - T3 : 0));
+            /* the period's noise values are the render kernel's business: step over them */
+            restart(vs_rng_gen(state_now(), (int)n_noise, lane, nullptr));
+        }
+
+        if (np >= st.tab_cap || nd > 65535u || T3 > 65535 || T4 > 65535) {
+            atomicExch(a.status, np >= st.tab_cap ? VS_ENOMEM : VS_ERANGE);
+            return;
+        }
+        if (lane == 0) {
+            VsPeriod e;
+            e.Ad = (double)A; e.Kd = (double)Knew; e.start = count;
+            e.T_np = (uint32_t)T | (nd << 16);
+            e.T34 = (uint32_t)T3 | ((uint32_t)T4 << 16);
+            e.ndw = ndw;
+            tab[np] = e;
+        }
+        count += (uint32_t)T;                                             /* :413 */
+        np++;
+    } while (count < st.n);                                               /* :423 */
+    if (lane == 0) a.n_periods[s] = np;
+}
+
 /* ================================================================================================
  * RENDER: one lane per (stream, chunk), one warp per 32 of them
  * ============================================================================================== */
@@ -406,43 +758,6 @@ struct __align__(16) VsSeg {
 __device__ __forceinline__ void vs_named_barrier(int id, int count)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-
-/* ---- noise: the warp steps ONE row's random() 31 values at a time ------------------------------------
- * glibc TYPE_3 is r[n] = r[n-31] + r[n-3] (mod 2^32), output r[n] >> 1.  With lane l < 31 holding
- * st[l] = r[n-31+l], the next 31 words are prefix sums along the three stride-3 chains:
- *     new[l] = st[l] + (l < 3 ? st[28+l] : new[l-3])
- * i.e. an inclusive scan with shuffle distances 3, 6, 12, 24 (chains are at most 11 long). */
-__device__ __forceinline__ uint32_t vs_rng_round(uint32_t st, int lane)
-{
-    const uint32_t wrap = __shfl_sync(VS_FULL, st, (lane + 28) & 31);
-    uint32_t v = st + (lane < 3 ? wrap : 0u), u;
-    u = __shfl_up_sync(VS_FULL, v, 3);  if (lane >= 3)  v += u;
-    u = __shfl_up_sync(VS_FULL, v, 6);  if (lane >= 6)  v += u;
-    u = __shfl_up_sync(VS_FULL, v, 12); if (lane >= 12) v += u;
-    u = __shfl_up_sync(VS_FULL, v, 24); if (lane >= 24) v += u;
-    return v;
-}
-
-/* advance the row's generator by m values; they go to out[0..m) when out is not NULL.  Returns the new
- * state (lanes 0..30).  m is warp-uniform. */
-__device__ __forceinline__ uint32_t vs_rng_gen(uint32_t st, int m, int lane, int32_t *out)
-{
-    int done = 0;
-    for (; m - done >= VS_RNG_DEG; done += VS_RNG_DEG) {
-        st = vs_rng_round(st, lane);
-        if (out && lane < VS_RNG_DEG) out[done + lane] = (int32_t)(st >> 1);
-    }
-    const int u = m - done;
-    if (u > 0) {                                     /* part of a round: the state window slides by u words */
-        const uint32_t nx = vs_rng_round(st, lane);
-        if (out && lane < u) out[done + lane] = (int32_t)(nx >> 1);
-        const int src = lane + u;
-        const uint32_t keep = __shfl_sync(VS_FULL, st, src & 31);
-        const uint32_t fresh = __shfl_sync(VS_FULL, nx, (src - VS_RNG_DEG) & 31);
-        st = src < VS_RNG_DEG ? keep : fresh;
-    }
-    return st;
 }
 
 /* ---- G: generate window w of the rows {row0, row0+step, ...} of a tile --------------------------------
@@ -888,8 +1203,12 @@ cudaError_t vs_launch_fp64_peak(double *scratch, int blocks, int iters, cudaStre
 /* ------------------------------------------------------------------------------------------------
  * launch wrappers (called from vs_api.cu)
  * ---------------------------------------------------------------------------------------------- */
-cudaError_t vs_launch_plan(const VsPlanArgs &a, bool want_log, cudaStream_t s)
+cudaError_t vs_launch_plan(const VsPlanArgs &a, bool want_log, bool warp_per_stream, cudaStream_t s)
 {
+    if (warp_per_stream && !want_log) {
+        vs_plan_warp_kernel<<<(a.n_streams + VS_PLANW_NT / 32 - 1) / (VS_PLANW_NT / 32), VS_PLANW_NT, 0, s>>>(a);
+        return cudaGetLastError();
+    }
     const unsigned grid = (a.n_streams + VS_PLAN_NT - 1) / VS_PLAN_NT;
     static_assert(VS_PLAN_SMEM >= VS_RNG_DEG * VS_PLAN_NT * 4, "plan kernel shared memory");
     if (want_log) {
