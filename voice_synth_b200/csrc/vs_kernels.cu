@@ -730,6 +730,11 @@ __device__ __forceinline__ int vs_quant_fast_nocheck(double v)
 #define VS_MAXSEG    4                     /* period segments a row can queue per bookkeeping pass */
 #define VS_TILE_I16  (32 * VS_TS)
 #define VS_THREADS_PAIRED ((VS_NP + VS_NP * VS_PW) * 32)
+/* flow mode with glottal noise: VS_PW warps per group, each doing G then W for its own rows (the noise is
+ * stepped row by row, one warp per 32 rows would be too few warps per SM) */
+#define VS_THREADS_FLOWN  (VS_NP * VS_PW * 32)
+#define VS_RENDER_THREADS(MODE, NOISE) ((MODE) != VS_MODE_FLOW ? VS_THREADS_PAIRED : ((NOISE) ? VS_THREADS_FLOWN : VS_NT))
+#define VS_RENDER_NPROD(MODE, NOISE) (((MODE) != VS_MODE_FLOW || (NOISE)) ? VS_PW : 1)
 
 /* one pitch period's share of one row's window: everything the cooperative evaluation needs (48 B) */
 struct __align__(16) VsSeg {
@@ -749,7 +754,7 @@ struct __align__(16) VsSeg {
 #define VS_SMEM_NSEG  (VS_NP * 32 * 4 + VS_NP * 32 * VS_MAXSEG * VS_SEGX * 4)   /* per-row segment counts + noise words */
 #define VS_ITEMS_BYTES (((32 * VS_MAXSEG * 4 + 4) * 2 + 15) & ~15)      /* work-item list of one producer warp */
 #define VS_SMEM_ITEMS(NPROD) (VS_NP * (NPROD) * VS_ITEMS_BYTES)
-#define VS_SMEM_BASE(NTILE) (VS_SMEM_TILES(NTILE) + VS_SMEM_LANES + VS_SMEM_SEGS + VS_SMEM_NSEG + VS_SMEM_ITEMS((NTILE) == 2 ? VS_PW : 1))
+#define VS_SMEM_BASE(NTILE) (VS_SMEM_TILES(NTILE) + VS_SMEM_LANES + VS_SMEM_SEGS + VS_SMEM_NSEG + VS_SMEM_ITEMS(VS_PW))
 /* noise: one RNG state per row, [NP][32 rows][32 words], oldest word first, and a
  * scratch of random() values per producer warp */
 #define VS_DRAW_SCRATCH 224                /* >= 7 rounds of 31 values >= VS_WIN */
@@ -1000,7 +1005,7 @@ __device__ __forceinline__ void vs_filter_window(uint32_t *row32, double (&y)[VS
 
 /* FLAGS: bit0 EXACT filter, bit1 RAW output, bit2 CHECKED quantiser */
 template <int MODE, bool NOISE, int FLAGS>
-__global__ void __launch_bounds__(MODE == VS_MODE_FLOW ? VS_NT : VS_THREADS_PAIRED, 1)
+__global__ void __launch_bounds__(VS_RENDER_THREADS(MODE, NOISE), 1)
 vs_render_kernel(const VsRenderArgs a)
 {
     constexpr bool PAIRED = MODE != VS_MODE_FLOW;
@@ -1018,20 +1023,21 @@ vs_render_kernel(const VsRenderArgs a)
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int pair = warp % VS_NP;                       /* warps 0..NP-1 consume, NP.. produce */
-    const int prod = PAIRED ? warp / VS_NP - 1 : 0;      /* producer index inside the group, -1 = consumer */
+    constexpr int NPROD = VS_RENDER_NPROD(MODE, NOISE);  /* producer warps per group */
+    const int prod = PAIRED ? warp / VS_NP - 1 : warp / VS_NP;   /* producer index inside the group, -1 = consumer */
     const bool consumer = PAIRED && warp < VS_NP;
-    const int step = PAIRED ? VS_PW : 1;                 /* a producer warp works rows prod, prod+step, ... */
+    const int step = NPROD;                              /* a producer warp works rows prod, prod+step, ... */
     int16_t *tile0 = s_tiles + pair * NTILE * VS_TILE_I16;
     VsLane *lanes = s_lanes + pair * 32;
     VsSeg *segs = s_segs + pair * 32 * VS_MAXSEG;
     int *nsegs = s_nseg + pair * (32 + 32 * VS_MAXSEG * VS_SEGX);
     uint32_t *rngrow = DRAWS ? s_rng + pair * 32 * 32 : nullptr;
     int32_t *scratch = DRAWS ? s_scratch + (pair * VS_PW + (prod > 0 ? prod : 0)) * VS_DRAW_SCRATCH : nullptr;
-    uint16_t *items = reinterpret_cast<uint16_t *>(s_items + (pair * (PAIRED ? VS_PW : 1) + (prod > 0 ? prod : 0)) * VS_ITEMS_BYTES);
+    uint16_t *items = reinterpret_cast<uint16_t *>(s_items + (pair * NPROD + (prod > 0 ? prod : 0)) * VS_ITEMS_BYTES);
     const int group_threads = (1 + VS_PW) * 32;
 
     /* Row of this lane.  Consumer lane l filters row l; producer lane l keeps the books of row
-     * prod + l*step (and, with noise, owns that row's RNG). */
+     * prod + l*step. */
     const int myrow = consumer ? lane : prod + lane * step;
     const uint32_t t = blockIdx.x * VS_NT + pair * 32 + (uint32_t)myrow;
     uint32_t chunk_id = (myrow < 32 && t < a.n_rows) ? a.order[t] : VS_NO_CHUNK;
@@ -1090,12 +1096,12 @@ vs_render_kernel(const VsRenderArgs a)
     }
 
     if (!PAIRED) {
-        /* ======== flow mode: one warp, G then W ======== */
+        /* ======== flow mode: every warp does G then W for its own rows ======== */
         __syncwarp();
         for (int w = 0; w < nwin; w++) {
-            vs_gen_tile<MODE, NOISE>(tile0, lanes, segs, nsegs, items, w, lane, 0, 1, me, q, rngrow, scratch);
+            vs_gen_tile<MODE, NOISE>(tile0, lanes, segs, nsegs, items, w, lane, prod, step, me, q, rngrow, scratch);
             __syncwarp();
-            for (int j = 0; j < 32; j++) vs_write_row(tile0 + j * VS_TS, lanes[j], w, lane);
+            for (int j = prod; j < 32; j += step) vs_write_row(tile0 + j * VS_TS, lanes[j], w, lane);
             __syncwarp();
         }
         return;
@@ -1227,7 +1233,7 @@ static void vs_go(const VsRenderArgs &a, cudaStream_t s)
     const unsigned grid = a.n_rows / VS_NT;
     const int dyn = VS_SMEM_BASE(MODE == VS_MODE_FLOW ? 1 : 2) + ((NOISE && MODE != VS_MODE_FILTER) ? VS_SMEM_NOISE : 0);
     cudaFuncSetAttribute(vs_render_kernel<MODE, NOISE, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-    vs_render_kernel<MODE, NOISE, FLAGS><<<grid, MODE == VS_MODE_FLOW ? VS_NT : VS_THREADS_PAIRED, dyn, s>>>(a);
+    vs_render_kernel<MODE, NOISE, FLAGS><<<grid, VS_RENDER_THREADS(MODE, NOISE), dyn, s>>>(a);
 }
 
 template <int MODE, bool NOISE>
