@@ -102,3 +102,29 @@ def test_batch_driver(tools, golden, tmp_path, oracle):
         want = oracle.vowel(oracle.flowgen(par), v["preset"])
         assert out.size == want.size
         assert np.abs(out.astype(np.int32) - want.astype(np.int32)).max() <= 1, c["name"]
+
+
+def test_batch_driver_slabs_and_writer_pool(tools, golden, tmp_path):
+    """N2: the manifest cut into slabs that alternate between two pinned buffers while writer threads put the
+    previous slab on disk -- same files as one slab, one writer"""
+    cases = [c for c in golden["cases"] if c["vowels"]]
+    lines = []
+    for rep in range(3):
+        for i, c in enumerate(cases):
+            lines.append(f"{{d}}/r{rep}_v{i}.wav {c['vowels'][0]['preset']} {c['seed'] + rep} {c['args']}")
+    outs = []
+    for name, extra in (("one", ["-S", "100000", "-W", "1"]), ("slabs", ["-S", "5", "-W", "4"])):
+        d = tmp_path / name
+        d.mkdir()
+        m = tmp_path / f"{name}.txt"
+        m.write_text("\n".join(lines).format(d=d) + "\n")
+        r = subprocess.run([str(tools / "vs_batch"), "-m", str(m)] + extra, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr + r.stdout
+        outs.append({f.name: f.read_bytes() for f in sorted(d.iterdir())})
+    assert len(outs[0]) == len(lines)
+    assert outs[0] == outs[1]
+    # unwritable output path: reported, non-zero exit
+    m = tmp_path / "bad.txt"
+    m.write_text(f"{tmp_path}/no_such_dir/x.wav a 1 -d 0.5\n")
+    r = subprocess.run([str(tools / "vs_batch"), "-m", str(m)], capture_output=True, text=True)
+    assert r.returncode != 0
