@@ -32,6 +32,10 @@ CASES = [
     ("M_noise_only", "-d 1 -f 180 -g 200 -n 0", [71], [("u", "")]),
     ("N_noise_kvar", "-d 1 -f 95 -n 25 -z 1 -j 2 -s 4 -k 0.55 -c 0.4", [81], [("2", "")]),
     ("O_upper", "-D 0.75 -F 140 -G 150 -J 2 -S 2 -A 9000", [91], [("a", "")]),
+    # closure speeds at which A*(K*cos - K + 1) leaves the 16-bit range after the first value below DC
+    ("P_k3", "-d 1 -f 120 -k 3 -j 1 -s 3", [101], [("a", "")]),
+    ("Q_k10_noise", "-d 1 -f 110 -k 10 -z 0.5 -s 5 -n 20", [102], [("i", "")]),
+    ("R_k2_amp30000_shimmer", "-d 1 -f 100 -k 2 -a 18000 -s 8 -l 0.05", [103], [("u", "")]),
 ]
 
 def sha(a):
@@ -58,7 +62,7 @@ def main():
             rec = {"name": name, "args": fargs, "seed": seed, "n": int(pcm.size), "sha256": sha(pcm),
                    "sum": int(pcm.astype(np.int64).sum()), "max": int(pcm.max()), "min": int(pcm.min()),
                    "head": pcm[:16].tolist(), "S_count": len(S), "S_head": S[:8], "snr_count": len(snr),
-                   "snr_head": snr[:8], "stdout_sha256": hashlib.sha256(txt.encode()).hexdigest(), "vowels": []}
+                   "snr_head": snr[:8], "vowels": []}
             for v, extra in vowels:
                 vp = O.ref_vowel(tmp + "/f.wav", v, seed, tmp, extra=extra.split())
                 rec["vowels"].append({"preset": v, "extra": extra, "sha256": sha(vp), "sum": int(vp.astype(np.int64).sum()),

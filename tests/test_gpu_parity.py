@@ -96,6 +96,25 @@ def test_plan_kernels_agree_on_random_batches(ctx, vs):
         assert np.array_equal(outs[0], outs[1]), make.__name__
 
 
+def test_steep_closure_wraps_like_the_reference_or_is_refused(ctx, vs, oracle):
+    """-k 3..20: A*(K*cos - K + 1) runs far below -32768 after the first value under DC; the reference has left the
+    falling branch by then (flowgen_shimmer.c:329), so nothing of the wrapped values may show.  -k 20000: the
+    16-bit cast wraps before the DC test, the reference's output is an accident -> VS_ERANGE"""
+    args = [["-d", "0.5", "-f", "120", "-k", "3", "-z", "0.5", "-j", "1", "-s", "3"],
+            ["-d", "0.5", "-f", "150", "-g", "160", "-k", "20", "-l", "0.1"],
+            ["-d", "0.5", "-f", "90", "-k", "6", "-s", "10", "-n", "15"]]
+    p = vs.FlowParams.from_cli(args, [5, 6, 7])
+    out, offs, ns = ctx.flowgen_batch(p)
+    for i in range(p.n):
+        want = oracle.flowgen(_oracle_par(oracle, vs, p, i))
+        got = out[int(offs[i]): int(offs[i]) + int(ns[i])]
+        assert np.array_equal(got, want), i
+    bad = vs.FlowParams.from_cli([["-d", "0.5", "-f", "120", "-k", "20000"]], [1])
+    with pytest.raises(vs.VsError) as e:
+        ctx.flowgen_batch(bad)
+    assert e.value.code == vs.VS_ERANGE
+
+
 def test_flowgen_chunked_equals_unchunked(ctx, vs, golden):
     cases, p = _golden_flow_params(golden, vs)
     ref, offs, ns = ctx.flowgen_batch(p)

@@ -220,6 +220,17 @@ int row_validate(const FlowRow &r, int *P_out = nullptr, uint64_t *n_out = nullp
     if (!std::isfinite(r.DC) || !(r.DC >= 0.0f) || r.DC > 32767.0f) return VS_ERANGE;
     if ((r.flags & VS_F_NOISE) && (!std::isfinite(r.noise) || !(r.noise > 0.0f))) return VS_ERANGE;
     if (r.flags & ~(VS_F_JITTER | VS_F_SHIMMER | VS_F_NOISE)) return VS_EINVAL;
+    /* Falling branch (:327-332): x = (short)ceil(A*(K*c - K + 1)), left at the first x < DC.  Between two samples
+     * the argument drops by at most A*K*2*sin(pi/(2*T2)); while that step stays below 2^15 the first value under DC
+     * still fits the short and the reference stops there.  Beyond it the cast wraps before the DC test and what
+     * the reference emits is an accident of 16-bit wrap-around: refused (hazards).  (A above 32767
+     * needs no bound: x[T2] = (short)ceil(A) is negative and the branch is left at once.) */
+    const int T2 = row_T2(r, P);
+    if (T2 >= 2) {
+        const double amax = std::min(32767.0, ((r.flags & VS_F_SHIMMER) && r.shimmer != 0.0f ? 1.8 : 1.0) * (double)r.amp);
+        const double kmax = (double)r.K * (1.0 + (double)r.Kvar);
+        if (amax * kmax * 2.0 * std::sin(3.141592653589793 / (2.0 * (double)T2)) > 32768.0) return VS_ERANGE;
+    }
     return VS_OK;
 }
 

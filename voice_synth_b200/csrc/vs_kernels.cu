@@ -892,15 +892,21 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
             for (int r = 0; r < 4; r++) {
                 const int it = items[b + r];
                 const VsSeg sg = segs[it & 127];                          /* row*VS_MAXSEG + segment */
-                const int o1 = min(sg.a1, 2 * sg.T2);                     /* T2 >= 1: the row has open-phase samples */
+                /* T2 >= 1: the row has open-phase samples.  A above 32767: x[T2] = (short)ceil(A) is negative,
+                 * the reference leaves the falling branch at once (:329) */
+                const int o1 = min(sg.a1, sg.Ad > 32767.0 ? sg.T2 : 2 * sg.T2);
                 const int i0 = sg.a0 + (it >> 7) * VS_ITEM_SAMPLES + lane; /* >= a0 >= 0 */
 #pragma unroll
                 for (int u = 0; u < VS_ITEM_SAMPLES / 32; u++) {
                     const int i = i0 + 32 * u;
                     const double tv = __ldg(sg.tab + min(i, 2 * sg.T2 - 1));
                     const double fall = __dadd_rn(__dsub_rn(__dmul_rn(sg.Kd, tv), sg.Kd), 1.0);
-                    const int v = vs_ceil_s16(__dmul_rn(sg.Ad, i < sg.T2 ? tv : fall));
-                    if (i < o1 && v >= sg.DCi) sg.out[i] = (int16_t)v;
+                    /* ceil as a 32-bit integer (host-side bounds keep it far from 2^31).  The reference tests the
+                     * value after its (short) cast: above 32767 it wraps negative, i.e. below DC; on the falling
+                     * branch the argument only decreases, so everything after the first value below DC is DC
+                     * too -- also where the short would have wrapped back above DC */
+                    const int v = __double2int_ru(__dmul_rn(sg.Ad, i < sg.T2 ? tv : fall));
+                    if (i < o1 && v >= sg.DCi && v <= 32767) sg.out[i] = (int16_t)v;
                 }
             }
         }
