@@ -171,6 +171,30 @@ def ncu_traffic():
     return None
 
 
+def bind_near_gpu(index):
+    """Run this rank on the CPUs of its GPU's NUMA node, so that the pinned host buffers it allocates are
+    node-local (first touch) and the PCM does not cross the socket interconnect after crossing PCIe.
+    Returns what was done, for the JSON line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int((pathlib.Path("/sys/bus/pci/devices") / bdf / "numa_node").read_text())
+        if node < 0:
+            return {"gpu": bdf, "node": node, "bound": False}
+        cpus = set()
+        for part in pathlib.Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        use = cpus & os.sched_getaffinity(0)
+        if not use:
+            return {"gpu": bdf, "node": node, "bound": False, "why": "no allowed CPU on that node"}
+        os.sched_setaffinity(0, use)
+        return {"gpu": bdf, "node": node, "bound": True, "cpus": len(use)}
+    except Exception as e:                                  # no sysfs, no such property: run unbound
+        return {"bound": False, "why": type(e).__name__}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -197,6 +221,7 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     torch.cuda.set_device(local_rank)
+    numa = bind_near_gpu(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -311,6 +336,7 @@ def main():
                               "counts": "useful + carry warm-up samples", "peak_source": "vs_measure_fp64_peak on this GPU",
                               "implied_sm_mhz": round(fp64_mhz)}},
         "clocks": clocks,
+        "numa": numa,
     }
     if world == 1 and args.cpu_sample > 0:
         try:
