@@ -1,24 +1,29 @@
 /* vs_kernels.cu -- sm_100a kernels of libvoicesynth_cuda.
  *
- *   vs_plan_kernel    one thread per STREAM, lock-step over pitch periods: the strictly sequential
- *                     part of flowgen_shimmer.c:246-423 -- glibc random() state, jitter and shimmer
- *                     random walks with their rejection loops, the closure-speed draw, and (with
- *                     -n) the pulse power and the number of noise draws.  Emits a period table and,
- *                     per time-chunk, the period the chunk starts in plus the RNG state there.
+ *   vs_plan_kernel       one THREAD per stream: the strictly sequential part of flowgen_shimmer.c:246-423
+ *                        -- glibc random() state, jitter and shimmer random walks with their rejection
+ *                        loops, the closure-speed draw, and (with -n) the pulse power and the number of
+ *                        noise draws.  Emits a period table and, per time-chunk, the period the chunk
+ *                        starts in plus the RNG state there.  The throughput form (many streams).
+ *   vs_plan_warp_kernel  the same table from one WARP per stream: random() 31 values per step by
+ *                        shuffles, the values' meanings worked out lane-parallel, the walk warp-uniform.
+ *                        The latency form (few or long streams, glottal noise).
  *
- *   vs_render_kernel  one LANE per (stream, time-chunk), one WARP per 32 of them, no block-level
- *                     synchronisation.  Per window of 96 samples the warp runs three phases over a
- *                     private shared-memory tile [32 rows][96 int16]:
- *                       G  generate: for each row in turn the 32 lanes evaluate 32 consecutive
- *                          samples of that stream.  Given the period table a sample is a pure
- *                          function of its index (flowgen_shimmer.c:319,328,335), so this phase is
- *                          divergence-free and closed-phase groups cost nothing.
- *                       F  filter: each lane runs the order-22 FP64 all-pole recurrence
- *                          (vowel_new.c:266-289) down its own row, in place.  The state is a
- *                          24-entry register ring, fully unrolled: ~25 FP64-pipe instructions per
- *                          sample with 22 independent products -> the FP64 pipe is the bound.
- *                       W  write: the warp stores the rows as whole 16-byte pieces, consecutive
- *                          lanes on consecutive pieces of a row (full 32-byte sectors).
+ *   vs_render_kernel     one row per (stream, time-chunk), 128 rows per CTA, no block-level
+ *                        synchronisation.  Per 32 rows ONE consumer warp and FOUR producer warps share
+ *                        two shared-memory tiles [32 rows][192 int16] through named barriers:
+ *                          G  generate (producers): given the period table a sample is a pure function
+ *                             of its index (flowgen_shimmer.c:319,328,335); lane-parallel bookkeeping
+ *                             queues per-period segments, the open phases are evaluated as flat lists
+ *                             of 64-sample work items, the closed phase is a word fill.
+ *                          F  filter (consumer): each lane runs the order-22 FP64 all-pole recurrence
+ *                             (vowel_new.c:266-289) down its own row, in place.  The state is a
+ *                             24-entry register ring, fully unrolled: ~25 FP64-pipe instructions per
+ *                             sample -> the FP64 pipe is the bound.
+ *                          W  write (producers): rows leave as whole 16-byte pieces, consecutive
+ *                             lanes on consecutive pieces of a row (full 32-byte sectors).
+ *                        Flow-only mode has no consumer: the producers do G then W.
+ *   vs_vnoise_kernel     vowel -n (vowel_new.c:302-324), one thread per stream.
  *
  * Every operation that decides an integer (period length, amplitude, sample value, draw count) is
  * written with explicit round-to-nearest intrinsics in the reference's evaluation order, so those
