@@ -729,17 +729,16 @@ __device__ __forceinline__ int vs_quant_fast_nocheck(double v)
 /* ---- shared-memory geometry of the render kernel ------------------------------------------------
  * A CTA serves VS_NP groups of 32 rows (one row = one stream-chunk).  In the filtering modes a group
  * is worked by one CONSUMER warp (F phase; warps 0..NP-1, one per SM sub-partition) and VS_PW
- * PRODUCER warps (G and W phases) over two tiles; in flow mode by a single warp doing G then W.   */
+ * PRODUCER warps (G and W phases) over two tiles; in flow mode by the VS_PW producer warps alone.  */
 #define VS_NP        4
 #define VS_PW        4
 #define VS_MAXSEG    4                     /* period segments a row can queue per bookkeeping pass */
 #define VS_TILE_I16  (32 * VS_TS)
 #define VS_THREADS_PAIRED ((VS_NP + VS_NP * VS_PW) * 32)
-/* flow mode with glottal noise: VS_PW warps per group, each doing G then W for its own rows (the noise is
- * stepped row by row, one warp per 32 rows would be too few warps per SM) */
-#define VS_THREADS_FLOWN  (VS_NP * VS_PW * 32)
-#define VS_RENDER_THREADS(MODE, NOISE) ((MODE) != VS_MODE_FLOW ? VS_THREADS_PAIRED : ((NOISE) ? VS_THREADS_FLOWN : VS_NT))
-#define VS_RENDER_NPROD(MODE, NOISE) (((MODE) != VS_MODE_FLOW || (NOISE)) ? VS_PW : 1)
+/* flow mode: no consumer; the VS_PW warps of a group each do G then W for their own rows (one warp per 32
+ * rows left the SM with 4-8 warps: 0.40 ms on the bench workload against 0.21 ms this way) */
+#define VS_THREADS_FLOW   (VS_NP * VS_PW * 32)
+#define VS_RENDER_THREADS(MODE) ((MODE) != VS_MODE_FLOW ? VS_THREADS_PAIRED : VS_THREADS_FLOW)
 
 /* one pitch period's share of one row's window: everything the cooperative evaluation needs (48 B) */
 struct __align__(16) VsSeg {
@@ -1016,7 +1015,7 @@ __device__ __forceinline__ void vs_filter_window(uint32_t *row32, double (&y)[VS
 
 /* FLAGS: bit0 EXACT filter, bit1 RAW output, bit2 CHECKED quantiser */
 template <int MODE, bool NOISE, int FLAGS>
-__global__ void __launch_bounds__(VS_RENDER_THREADS(MODE, NOISE), 1)
+__global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), 1)
 vs_render_kernel(const VsRenderArgs a)
 {
     constexpr bool PAIRED = MODE != VS_MODE_FLOW;
@@ -1034,7 +1033,7 @@ vs_render_kernel(const VsRenderArgs a)
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int pair = warp % VS_NP;                       /* warps 0..NP-1 consume, NP.. produce */
-    constexpr int NPROD = VS_RENDER_NPROD(MODE, NOISE);  /* producer warps per group */
+    constexpr int NPROD = VS_PW;                         /* producer warps per group */
     const int prod = PAIRED ? warp / VS_NP - 1 : warp / VS_NP;   /* producer index inside the group, -1 = consumer */
     const bool consumer = PAIRED && warp < VS_NP;
     const int step = NPROD;                              /* a producer warp works rows prod, prod+step, ... */
@@ -1244,7 +1243,7 @@ static void vs_go(const VsRenderArgs &a, cudaStream_t s)
     const unsigned grid = a.n_rows / VS_NT;
     const int dyn = VS_SMEM_BASE(MODE == VS_MODE_FLOW ? 1 : 2) + ((NOISE && MODE != VS_MODE_FILTER) ? VS_SMEM_NOISE : 0);
     cudaFuncSetAttribute(vs_render_kernel<MODE, NOISE, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-    vs_render_kernel<MODE, NOISE, FLAGS><<<grid, VS_RENDER_THREADS(MODE, NOISE), dyn, s>>>(a);
+    vs_render_kernel<MODE, NOISE, FLAGS><<<grid, VS_RENDER_THREADS(MODE), dyn, s>>>(a);
 }
 
 template <int MODE, bool NOISE>
