@@ -824,10 +824,19 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 pa.log = want_log ? sl.log.p : nullptr;
                 pa.status = (int32_t *)sl.status[cp].p;
                 pa.need_pulse = want_log;
-                /* one warp per stream while the batch is too small to fill the GPU with one thread per stream;
-                 * with glottal noise (hundreds of serial pulse samples and draws per period and thread) that
-                 * holds for much larger batches */
-                const bool plan_warps = ctx->opt_plan_warps < 0 ? pa.n_streams <= (any_noise ? VS_PLAN_WARP_MAX_NOISE : VS_PLAN_WARP_MAX) : ctx->opt_plan_warps != 0;
+                /* One warp per stream while the batch is too small to fill the GPU with one thread per stream
+                 * (measured crossover on B200: ~8 k streams, ~14 k with glottal noise, where a thread walks
+                 * hundreds of serial pulse samples and draws per period).  The warp form issues ~7x the
+                 * instructions, though: when the previous call is still rendering it would take issue slots
+                 * from the FP64-bound render warps, while the thread form hides on its own SMs -- so with a
+                 * call in flight only really small batches take it. */
+                bool plan_warps;
+                if (ctx->opt_plan_warps >= 0) plan_warps = ctx->opt_plan_warps != 0;
+                else {
+                    const bool busy = cudaEventQuery(sl.call_done[(cp + VS_DEPTH - 1u) % VS_DEPTH]) == cudaErrorNotReady;
+                    (void)cudaGetLastError();
+                    plan_warps = pa.n_streams <= (any_noise ? VS_PLAN_WARP_MAX_NOISE : busy ? VS_PLAN_WARP_MAX : VS_PLAN_WARP_MAX_IDLE);
+                }
                 CU(vs_launch_plan(pa, want_log, plan_warps, sl.plan));
                 ctx->timing.launches++;
             }

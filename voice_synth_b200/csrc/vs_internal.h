@@ -13,8 +13,10 @@
                                   issue slots by the render warps of call k (measured: 0.35 -> 0.7 ms)        */
 #define VS_PLAN_SMEM (96 * 1024)
 #define VS_PLAN_SMS  8
-#define VS_PLAN_WARP_MAX 1024   /* batches up to this many streams get one WARP per stream in the plan kernel */
-#define VS_PLAN_WARP_MAX_NOISE 16384   /* same, when some streams carry glottal noise */
+/* batches up to this many streams get one WARP per stream in the plan kernel (vs_api.cu, plan launch) */
+#define VS_PLAN_WARP_MAX       1024    /* while the previous call is still on the GPU */
+#define VS_PLAN_WARP_MAX_IDLE  6144    /* GPU idle: the plan kernel is the call's critical path */
+#define VS_PLAN_WARP_MAX_NOISE 12288   /* some streams carry glottal noise */
 #define VS_RNG_DEG 31          /* glibc TYPE_3 */
 #define VS_NO_CHUNK 0xffffffffu
 #define VS_WIN     192         /* samples per stream per render window (8 ring blocks, 24 x 16 B)  */
