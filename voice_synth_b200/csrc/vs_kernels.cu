@@ -321,6 +321,23 @@ __device__ __forceinline__ uint32_t vs_rng_round(uint32_t st, int lane)
     return v;
 }
 
+/* srandom() for the warp-cooperative generator: every lane runs the 30 Schrage steps and keeps the word that
+ * is (lane)-th oldest once f = 3, i.e. word (lane+3) mod 31; the 310 discarded values are 10 rounds. */
+__device__ __forceinline__ uint32_t vs_rng_seed_warp(uint32_t seed, int lane)
+{
+    int32_t w = (int32_t)(seed ? seed : 1u);
+    const int want = (lane + 3) % VS_RNG_DEG;
+    uint32_t rs = (uint32_t)w;
+    for (int i = 1; i < VS_RNG_DEG; i++) {
+        const int32_t hi = w / 127773, lo = w % 127773;
+        w = 16807 * lo - 2836 * hi;
+        if (w < 0) w += 2147483647;
+        if (i == want) rs = (uint32_t)w;
+    }
+    for (int k = 0; k < 10; k++) rs = vs_rng_round(rs, lane);
+    return rs;
+}
+
 /* advance the row's generator by m values; they go to out[0..m) when out is not NULL.  Returns the new
  * state (lanes 0..30).  m is warp-uniform. */
 __device__ __forceinline__ uint32_t vs_rng_gen(uint32_t st, int m, int lane, int32_t *out)
@@ -412,21 +429,7 @@ __global__ void __launch_bounds__(VS_PLANW_NT) vs_plan_warp_kernel(const VsPlanA
     const int DCi = (int)ceilf(st.DC);
     const int DCs = st.DCs;
 
-    /* srandom (flowgen_shimmer.c:241): every lane runs the 30 Schrage steps, lane l keeps the word that is
-     * l-th oldest once f = 3, i.e. word (l+3) mod 31; then the 310 discarded values = 10 rounds */
-    uint32_t rs;
-    {
-        int32_t w = (int32_t)(st.seed ? st.seed : 1u);
-        const int want = (lane + 3) % VS_RNG_DEG;
-        rs = (uint32_t)w;
-        for (int i = 1; i < VS_RNG_DEG; i++) {
-            const int32_t hi = w / 127773, lo = w % 127773;
-            w = 16807 * lo - 2836 * hi;
-            if (w < 0) w += 2147483647;
-            if (i == want) rs = (uint32_t)w;
-        }
-        for (int k = 0; k < 10; k++) rs = vs_rng_round(rs, lane);
-    }
+    uint32_t rs = vs_rng_seed_warp(st.seed, lane);                       /* flowgen_shimmer.c:241 */
 
     /* Value source.  Values are numbered from the last reset; value i lives in ring slot i & 63.
      * rs = generator state before round A; nxa = round A = values [base, base+31); nxb = round B =
@@ -1159,39 +1162,62 @@ vs_render_kernel(const VsRenderArgs a)
 }
 
 /* ================================================================================================
- * vowel -n: output noise, one thread per stream, in place (vowel_new.c:302-324)
+ * vowel -n: output noise in place (vowel_new.c:302-324), one WARP per stream.
+ * Per frame of `frame` samples: the float power sum runs in sample order (not associative: every lane
+ * adds the same 32 squares, staged through shared memory); the frame's random() values come 31 at a time
+ * (vs_rng_gen) into a per-warp scratch and the noise is added lane-parallel.
  * ============================================================================================== */
-__global__ void __launch_bounds__(VS_NT) vs_vnoise_kernel(int16_t *pcm, const VsNoiseRow *rows, uint32_t n_rows)
+#define VS_VN_NT      128
+#define VS_VN_SCRATCH 1024            /* random() values per piece of a frame */
+
+__global__ void __launch_bounds__(VS_VN_NT) vs_vnoise_kernel(int16_t *pcm, const VsNoiseRow *rows, uint32_t n_rows)
 {
-    __shared__ uint32_t s_rng[VS_RNG_DEG * VS_NT];
-    const uint32_t s = blockIdx.x * VS_NT + threadIdx.x;
+    __shared__ int32_t s_draws[VS_VN_NT / 32][VS_VN_SCRATCH];
+    __shared__ __align__(16) float s_sq[VS_VN_NT / 32][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t s = blockIdx.x * (VS_VN_NT / 32) + wib;
     if (s >= n_rows) return;
     const VsNoiseRow r = rows[s];
     if (!(r.snr > 0.0f) || r.frame == 0) return;
-    VsRng g;
-    g.r = s_rng + threadIdx.x;
-    vs_rng_seed(g, r.seed);                                              /* :234 */
+    int32_t *draws = s_draws[wib];
+    float *sqb = s_sq[wib];
+    uint32_t st = vs_rng_seed_warp(r.seed, lane);                        /* :234 */
     int16_t *y = pcm + r.off;
     for (uint32_t base = 0; base < r.n; base += r.frame) {
         const uint32_t ni = min(r.frame, r.n - base);
         float aux = 0.0f;
-        for (uint32_t i = 0; i < ni; i++) {                              /* :304-306, float, in order */
-            const float v = (float)y[base + i];
-            aux = __fadd_rn(aux, __fmul_rn(v, v));
+        for (uint32_t b0 = 0; b0 < ni; b0 += 32) {                       /* :304-306, float, in order */
+            const uint32_t i = b0 + lane;
+            const float v = i < ni ? (float)y[base + i] : 0.0f;
+            sqb[lane] = __fmul_rn(v, v);                                 /* +0.0f beyond the frame: adds nothing */
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float4 q = reinterpret_cast<const float4 *>(sqb)[k];
+                aux = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(aux, q.x), q.y), q.z), q.w);
+            }
+            __syncwarp();
         }
         const float sig_power = __fdiv_rn(aux, (float)(int16_t)ni);      /* `ni` is a signed short (:65) */
         const float width = __double2float_rn(sqrt((double)__fdiv_rn(__fmul_rn(12.0f, sig_power), r.snr)));   /* :309 */
-        for (uint32_t i = 0; i < ni; i++) {                              /* :314-319 */
-            const float nv = __double2float_rn(vs_div_const((double)vs_rng_next(g), VS_RAND_MAX_D, VS_INV_RM));
-            const float a = __double2float_rn(__dmul_rn((double)width, __dsub_rn((double)nv, 0.5)));
-            y[base + i] = (int16_t)vs_round2int(__dadd_rn((double)y[base + i], (double)a));
+        for (uint32_t p0 = 0; p0 < ni; p0 += VS_VN_SCRATCH) {            /* :314-319 */
+            const uint32_t m = min((uint32_t)VS_VN_SCRATCH, ni - p0);
+            st = vs_rng_gen(st, (int)m, lane, draws);
+            __syncwarp();
+            for (uint32_t k = lane; k < m; k += 32) {
+                const float nv = __double2float_rn(vs_div_const((double)draws[k], VS_RAND_MAX_D, VS_INV_RM));
+                const float a = __double2float_rn(__dmul_rn((double)width, __dsub_rn((double)nv, 0.5)));
+                int16_t *dst = y + base + p0 + k;
+                *dst = (int16_t)vs_round2int(__dadd_rn((double)*dst, (double)a));
+            }
+            __syncwarp();
         }
     }
 }
 
 cudaError_t vs_launch_vnoise(int16_t *pcm, const VsNoiseRow *rows, uint32_t n_rows, cudaStream_t s)
 {
-    vs_vnoise_kernel<<<(n_rows + VS_NT - 1) / VS_NT, VS_NT, 0, s>>>(pcm, rows, n_rows);
+    vs_vnoise_kernel<<<(n_rows + VS_VN_NT / 32 - 1) / (VS_VN_NT / 32), VS_VN_NT, 0, s>>>(pcm, rows, n_rows);
     return cudaGetLastError();
 }
 
