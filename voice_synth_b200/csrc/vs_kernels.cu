@@ -930,17 +930,21 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
                     const uint32_t *x = segx + (j * VS_MAXSEG + sidx) * VS_SEGX;
                     const int T3 = (int)(x[0] & 0xffffu), T4 = (int)(x[0] >> 16);
                     const int ndw = (int)x[1], skip = (int)x[2];
-                    if (skip) st = vs_rng_gen(st, skip, lane, nullptr);
                     /* the period's noise samples inside this window, in draw order: [.., T4) then [T3, ..) */
                     const int n1hi = min(sg.a1, T4), n2lo = max(sg.a0, T3);
                     const int c1 = max(0, n1hi - sg.a0), c2 = max(0, sg.a1 - n2lo);
-                    if (c1 + c2 > 0) {
-                        st = vs_rng_gen(st, c1 + c2, lane, scratch);
+                    /* the perturbation draws to step over come first; a few of them ride along in the scratch */
+                    int lead = 0;
+                    if (skip > 0 && skip + c1 + c2 <= VS_DRAW_SCRATCH) lead = skip;
+                    else if (skip > 0) st = vs_rng_gen(st, skip, lane, nullptr);
+                    if (lead + c1 + c2 > 0) {
+                        st = vs_rng_gen(st, lead + c1 + c2, lane, scratch);
                         __syncwarp();
+                        const int32_t *d1 = scratch + lead - sg.a0, *d2 = scratch + lead + c1 - n2lo;
                         for (int i = sg.a0 + lane; i < n1hi; i += 32)
-                            sg.out[i] = (int16_t)vs_add_clip(sg.out[i], vs_noise_w(scratch[i - sg.a0], ndw));
+                            sg.out[i] = (int16_t)vs_add_clip(sg.out[i], vs_noise_w(d1[i], ndw));
                         for (int i = n2lo + lane; i < sg.a1; i += 32)
-                            sg.out[i] = (int16_t)vs_add_clip(sg.out[i], vs_noise_w(scratch[c1 + i - n2lo], ndw));
+                            sg.out[i] = (int16_t)vs_add_clip(sg.out[i], vs_noise_w(d2[i], ndw));
                         __syncwarp();
                     }
                 }
