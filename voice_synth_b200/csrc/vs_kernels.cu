@@ -941,10 +941,22 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
                         st = vs_rng_gen(st, lead + c1 + c2, lane, scratch);
                         __syncwarp();
                         const int32_t *d1 = scratch + lead - sg.a0, *d2 = scratch + lead + c1 - n2lo;
-                        for (int i = sg.a0 + lane; i < n1hi; i += 32)
-                            sg.out[i] = (int16_t)vs_add_clip(sg.out[i], vs_noise_w(d1[i], ndw));
-                        for (int i = n2lo + lane; i < sg.a1; i += 32)
-                            sg.out[i] = (int16_t)vs_add_clip(sg.out[i], vs_noise_w(d2[i], ndw));
+                        /* two samples per lane and step: the chains (load, divide, scale, ceil, add, clip) are
+                         * long and independent */
+                        for (int i = sg.a0 + lane; i < n1hi; i += 64) {
+                            const int i2 = i + 32;
+                            const bool two = i2 < n1hi;
+                            const int wa = vs_noise_w(d1[i], ndw), wb = vs_noise_w(d1[two ? i2 : i], ndw);
+                            sg.out[i] = (int16_t)vs_add_clip(sg.out[i], wa);
+                            if (two) sg.out[i2] = (int16_t)vs_add_clip(sg.out[i2], wb);
+                        }
+                        for (int i = n2lo + lane; i < sg.a1; i += 64) {
+                            const int i2 = i + 32;
+                            const bool two = i2 < sg.a1;
+                            const int wa = vs_noise_w(d2[i], ndw), wb = vs_noise_w(d2[two ? i2 : i], ndw);
+                            sg.out[i] = (int16_t)vs_add_clip(sg.out[i], wa);
+                            if (two) sg.out[i2] = (int16_t)vs_add_clip(sg.out[i2], wb);
+                        }
                         __syncwarp();
                     }
                 }
