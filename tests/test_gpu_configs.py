@@ -181,3 +181,54 @@ def test_multi_device_context(vs, oracle):
     finally:
         one.close()
         two.close()
+
+
+def test_random_parameter_fuzz(ctx, vs, oracle):
+    """~300 voices with every knob drawn at random inside the reference's accepted ranges (five sampling rates,
+    noise on half of them, closure speeds up to 6, DC offsets, random gain/pre-emphasis), both plan kernels,
+    chunked and unchunked: flow bit-exact and PCM within 1 LSB of the oracle for EVERY stream"""
+    rng = np.random.default_rng(20261018)
+    n = 300
+    args, seeds = [], []
+    for i in range(n):
+        fs = int(rng.choice([8000, 11025, 16000, 22051, 44100]))        # -r 22050 is rejected by the reference CLI itself
+        f0 = float(rng.uniform(70, 330))
+        a = ["-r", str(fs), "-d", f"{rng.uniform(0.5, 1.3):.3f}", "-f", f"{f0:.2f}", "-g", f"{f0 + 20:.2f}"]
+        if rng.random() < 0.8:
+            a += ["-j", f"{rng.uniform(0, 6):.2f}"]
+        if rng.random() < 0.8:
+            a += ["-s", f"{rng.uniform(0, 25):.2f}"]
+        if rng.random() < 0.5:
+            a += ["-n", f"{rng.uniform(3, 45):.1f}"]
+        if rng.random() < 0.5:
+            a += ["-c", f"{rng.uniform(0.25, 0.95):.3f}"]
+        if rng.random() < 0.5:
+            a += ["-k", f"{rng.uniform(0.5, 6):.3f}"]
+        if rng.random() < 0.4:
+            a += ["-z", f"{rng.uniform(0, 1):.3f}"]
+        if rng.random() < 0.4:
+            a += ["-l", f"{rng.uniform(0, 0.29):.3f}"]
+        if rng.random() < 0.5:
+            a += ["-a", str(int(rng.integers(500, 18000)))]
+        args.append(a)
+        seeds.append(int(rng.integers(0, 2**32)))
+    p = vs.FlowParams.from_cli(args, seeds)
+    # steep closures on very short pitch periods fall outside the defined range (VS_ERANGE): drop those voices
+    keep = [i for i in range(n) if vs.flow_validate(p.select(np.array([i])))[0] == vs.VS_OK]
+    assert len(keep) > 0.9 * n
+    p = p.select(np.array(keep))
+    n = p.n
+    f = vs.FilterParams(n)
+    f.preset[...] = [ord("aiu1234567"[int(k)]) for k in rng.integers(0, 10, n)]
+    f.gain[...] = rng.uniform(1.0, 20.0, n).astype(np.float32)
+    f.pre[...] = rng.uniform(0.0, 1.0, n).astype(np.float32)
+    for warps, chunk in ((0, 0), (1, 0), (-1, 1536)):
+        ctx.set_option(vs.OPT_PLAN_WARPS, warps)
+        ctx.set_option(vs.OPT_CHUNK_SAMPLES, chunk)
+        try:
+            flow, foffs, ns = ctx.flowgen_batch(p)
+            pcm, offs, _ = ctx.synth_batch(p, f)
+        finally:
+            ctx.set_option(vs.OPT_PLAN_WARPS, -1)
+            ctx.set_option(vs.OPT_CHUNK_SAMPLES, 0)
+        _check_sample(oracle, vs, p, f, pcm, offs, ns, range(n), flow, foffs)

@@ -203,6 +203,13 @@ class FilterParams:
         return c
 
 
+def flow_validate(p):
+    """(VS_OK, None) or (error code, index of the first offending stream): the checks vs_*_batch apply up front."""
+    bad = C.c_size_t(0)
+    rc = _lib.load().vs_flow_validate(C.byref(p._c()), p.n, C.byref(bad))
+    return (rc, None) if rc == 0 else (rc, int(bad.value))
+
+
 def flow_nsamples(p):
     out = np.zeros(p.n, dtype=np.uint64)
     _lib.load().vs_flow_nsamples(C.byref(p._c()), p.n, out.ctypes.data)
