@@ -508,16 +508,58 @@ __global__ void __launch_bounds__(VS_PLANW_NT) vs_plan_warp_kernel(const VsPlanA
     VsPeriod *tab = a.table + st.tab_off;
     VsChunk *chunks = a.chunks + st.chunk0;
     uint32_t next_target = st.n_chunks ? chunks[0].gen_target : 0xffffffffu;
+    /* the target after that is fetched one mark ahead: a single long stream crosses a chunk start every few
+     * periods and would otherwise wait for a dependent global load each time */
+    uint32_t after_target = st.n_chunks > 1 ? chunks[1].gen_target : 0xffffffffu;
     int guard = 0;
     const bool both = do_jit && do_shm;
 
     do {
+        /* Tight loop for the common stream (jitter and shimmer on, no noise) while everything goes the common
+         * way: three values per period straight off the ring, both draws accepted, divisions conclusive.  It
+         * leaves to the general period below for anything else -- values running out (refill), a rejected
+         * draw, an inconclusive division -- and comes back afterwards. */
+        if (both && !noise) {
+            const int lim = base + (have_b ? 2 * VS_RNG_DEG : VS_RNG_DEG);
+            while (pos + 3 <= lim && count < st.n && np < st.tab_cap) {
+                const int pj = pos & 63, ps = (pos + 1) & 63, pk = (pos + 2) & 63;
+                const double numj = __dmul_rn((double)dper, itp[0][pj]);
+                const double nums = __dmul_rn((double)dsh, itp[4][ps]);
+                bool dj, ds;
+                const double qj = vs_div_checked_y(numj, itp[1][pj], itp[2][pj], dj);
+                const double qs = vs_div_checked_y(nums, itp[5][ps], itp[6][ps], ds);
+                const float curJ = __double2float_rn(__dadd_rn(qj, itp[3][pj]));
+                const float curS = __double2float_rn(__dadd_rn(qs, itp[7][ps]));
+                const float Tf = ceilf(__fadd_rn(Pf, curJ));
+                const float An = __fadd_rn(ampf, curS);
+                if (dj || ds || Tf > t_hi || Tf < t_lo || !(Tf >= 1.0f && Tf <= 32767.0f) || An > a_hi || An < a_lo) break;
+                dper = curJ; dsh = curS; T = (int)Tf;
+                pos += 3;
+                while (next_target < count + (uint32_t)T) {
+                    if (lane == 0) chunks[next_c].first_period = np;
+                    next_c++;
+                    next_target = after_target;
+                    after_target = next_c + 1 < st.n_chunks ? chunks[next_c + 1].gen_target : 0xffffffffu;
+                }
+                if (lane == 0) {
+                    VsPeriod e;
+                    e.Ad = (double)An; e.Kd = (double)kn[pk]; e.start = count;
+                    e.T_np = (uint32_t)T | (3u << 16);
+                    e.T34 = (uint32_t)(2 * T2);
+                    e.ndw = 0;
+                    tab[np] = e;
+                }
+                count += (uint32_t)T;
+                np++;
+            }
+            if (count >= st.n) break;
+        }
         uint32_t nd = 0;
         float A = ampf, Knew = 0.0f;
         bool committed = false;
         /* without noise the values of consecutive periods are consecutive: keep a round in reserve so that
-         * the common case below never meets a round boundary */
-        refill(!noise);
+         * the common case never meets a round boundary */
+        if (pos >= base + VS_RNG_DEG || !(noise || have_b)) refill(!noise);
         /* Common case first: jitter and shimmer both on, every draw accepted at once.  The two random walks
          * are independent recurrences, so their division chains run side by side; acceptance is tested on
          * ceilf(P + dPer), the same integer as (short)ceil((double)..) when it is in range.  Anything else
@@ -589,7 +631,8 @@ __global__ void __launch_bounds__(VS_PLANW_NT) vs_plan_warp_kernel(const VsPlanA
                 if (lane < VS_RNG_DEG) a.rng_snap[(size_t)(st.chunk0 + next_c) * 32 + (lane + 3) % VS_RNG_DEG] = now;
             }
             next_c++;
-            next_target = next_c < st.n_chunks ? chunks[next_c].gen_target : 0xffffffffu;
+            next_target = after_target;
+            after_target = next_c + 1 < st.n_chunks ? chunks[next_c + 1].gen_target : 0xffffffffu;
         }
 
         int T3 = 2 * T2;
@@ -642,7 +685,7 @@ __global__ void __launch_bounds__(VS_PLANW_NT) vs_plan_warp_kernel(const VsPlanA
             restart(vs_rng_gen(state_now(), (int)n_noise, lane, nullptr));
         }
 
-        if (np >= st.tab_cap || nd > 65535u || T3 > 65535 || T4 > 65535) {
+        if (np >= st.tab_cap || (!committed && nd > 65535u) || (noise && (T3 > 65535 || T4 > 65535))) {
             atomicExch(a.status, np >= st.tab_cap ? VS_ENOMEM : VS_ERANGE);
             return;
         }
