@@ -429,10 +429,11 @@ void plan_filter_chunks(vs_ctx *ctx, const Slot &slot, const std::vector<VsStrea
         classes[{hs[a0 + i].n, hs[a0 + i].preset}]++;
         nmax = std::max(nmax, hs[a0 + i].n);
     }
+    /* the first chunk of a stream needs no warm-up, so it emits `budget` samples, the others budget - W */
     auto chunks_of = [&](uint32_t n, uint8_t preset, double budget) -> uint32_t {
         if ((double)n <= budget) return 1u;
         const double L = std::max(512.0, budget - (double)ctx->warm[preset]);
-        return (uint32_t)std::ceil((double)n / L);
+        return 1u + (uint32_t)std::ceil(((double)n - budget) / L);
     };
     auto rows_for = [&](double budget) -> double {
         double rows = 0;
@@ -616,24 +617,36 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 /* host outputs are mirrored on the device at the same offsets relative to a 16-byte
                  * aligned slab base, so the phase of a row is its sample offset mod 8 either way */
                 const uint32_t ph = (uint32_t)(base_addr & 7);
-                uint32_t C, L;
+                const uint32_t W = (b.mode == VS_MODE_FLOW) ? 0u : (uint32_t)ctx->warm[s.preset];
+                /* chunk c > 0 emits [L0 + (c-1)*L - ph, L0 + c*L - ph); L0 and L are multiples of 8 */
+                uint32_t C, L, L0;
                 if (b.mode == VS_MODE_FLOW) {
-                    L = Lflow;
+                    L = L0 = Lflow;
                     C = (L == 0 || s.n <= L) ? 1u : (uint32_t)((s.n + L - 1) / L);
                 } else {
                     C = nch[i - a0];
-                    L = C <= 1 ? 0u : (uint32_t)(((s.n + C - 1) / C + 7u) & ~7u);     /* equal chunks, multiple of 8 */
-                    if (C > 1) C = (uint32_t)((s.n + L - 1) / L);
+                    L = L0 = 0u;
+                    if (C > 1) {
+                        if (ctx->opt_chunk == 0 && (uint64_t)s.n > (uint64_t)W + 64ull * C) {       /* auto planning */
+                            /* equal WORK per row: the first chunk has no warm-up and emits W samples more */
+                            L = (uint32_t)(((s.n - W + C - 1) / C + 7u) & ~7u);
+                            const uint32_t rest = (C - 1) * L;
+                            L0 = rest < s.n ? ((s.n - rest + 7u) & ~7u) : 0u;
+                        }
+                        if (L0 == 0u || L0 < L) {                      /* stream barely longer than the warm-up: equal chunks */
+                            L = L0 = (uint32_t)(((s.n + C - 1) / C + 7u) & ~7u);
+                        }
+                        C = s.n <= L0 ? 1u : 1u + (uint32_t)((s.n - L0 + L - 1) / L);
+                    }
                 }
                 sl.plan_nch[i - s0] = C;
                 tab_total += s.tab_cap;
-                const uint32_t W = (b.mode == VS_MODE_FLOW) ? 0u : (uint32_t)ctx->warm[s.preset];
                 for (uint32_t c = 0; c < C; c++) {
                     VsChunk ck;
                     memset(&ck, 0, sizeof ck);
                     ck.stream = (uint32_t)(i - s0);
-                    ck.emit_lo = c == 0 ? 0u : c * L - ph;
-                    ck.emit_hi = c + 1 == C ? s.n : (c + 1) * L - ph;
+                    ck.emit_lo = c == 0 ? 0u : L0 + (c - 1) * L - ph;
+                    ck.emit_hi = c + 1 == C ? s.n : L0 + c * L - ph;
                     ck.gen_target = ck.emit_lo > W ? ck.emit_lo - W : 0u;
                     if (c > 0) warm_total += ck.emit_lo - ck.gen_target;
                     hc.push_back(ck);
