@@ -729,7 +729,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         if (b.mode != VS_MODE_FILTER) {
             if ((rc = dev_reserve(ctx, sl, sl.table[cp], (tab_total + 8) * sizeof(VsPeriod)))) return rc;
             if (any_noise && (rc = dev_reserve(ctx, sl, sl.snap[cp], nc * 32 * sizeof(uint32_t)))) return rc;
-            if ((rc = dev_reserve(ctx, sl, sl.costab, std::max<size_t>(8, ctx->cos_host.size() * sizeof(double))))) return rc;
+            if ((rc = dev_reserve(ctx, sl, sl.costab, (ctx->cos_host.size() + VS_COS_SLACK) * sizeof(double)))) return rc;
             if (sl.costab_uploaded != ctx->cos_host.size()) {
                 /* tables only ever grow; a synchronous copy keeps the host vector free to grow again */
                 /* stream-ordered on the plan stream (a plain cudaMemcpy from pageable memory may still be in

@@ -786,13 +786,15 @@ __device__ __forceinline__ int vs_quant_fast_nocheck(double v)
 #define VS_THREADS_FLOW   (VS_NP * VS_PW * 32)
 #define VS_RENDER_THREADS(MODE) ((MODE) != VS_MODE_FLOW ? VS_THREADS_PAIRED : VS_THREADS_FLOW)
 
-/* one pitch period's share of one row's window: everything the cooperative evaluation needs (48 B) */
+/* one pitch period's share of one row's window: everything the cooperative evaluation needs (48 B).
+ * The evaluation counts samples k = 0.. from the segment's first in-window sample a0. */
 struct __align__(16) VsSeg {
     double Ad, Kd;
-    const double *tab;   /* h[0..T2) then c[0..T2) of the row's T2 */
-    int16_t *out;        /* tile address of the period's sample 0 (only in-window indices are touched) */
-    int a0, a1;          /* in-period indices [a0,a1) that fall into this window  */
-    int T2, DCi;
+    const double *tab;   /* table entry of sample a0 (h[0..T2) then c[0..T2) of the row's T2) */
+    int16_t *out;        /* tile address of sample a0 */
+    uint32_t nr;         /* low 16 bits: open-phase samples to evaluate from a0 on; high 16: how many of them rise */
+    int DCi;
+    int a0, a1;          /* in-period indices [a0,a1) that fall into this window (noise pass) */
 };
 #define VS_ITEM_SAMPLES 64                 /* open-phase samples per work item: two per lane */
 
@@ -885,12 +887,16 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
                 const int pend = e.start + e.T;
                 if (pend > glo) {
                     const int a0 = max(0, glo - e.start), a1 = min(e.T, ghi - e.start);
-                    const int nopen = min(a1, open_end) - a0;
+                    /* A above 32767: x[T2] = (short)ceil(A) is negative, the reference leaves the falling
+                     * branch at once (:329) */
+                    const int nopen = min(a1, e.Ad > 32767.0 ? mine.T2 : open_end) - a0;
                     if (nopen > 0 || (NOISE && mine.noise)) {
                         VsSeg sg;
-                        sg.Ad = e.Ad; sg.Kd = e.Kd; sg.tab = mine.ct;
-                        sg.out = tile + myrow * VS_TS + (e.start - wb_m);
-                        sg.a0 = a0; sg.a1 = a1; sg.T2 = mine.T2; sg.DCi = mine.DCi;
+                        sg.Ad = e.Ad; sg.Kd = e.Kd; sg.tab = mine.ct + a0;
+                        sg.out = tile + myrow * VS_TS + (e.start - wb_m) + a0;
+                        sg.nr = (uint32_t)max(nopen, 0) | ((uint32_t)min(max(mine.T2 - a0, 0), VS_WIN) << 16);
+                        sg.DCi = mine.DCi;
+                        sg.a0 = a0; sg.a1 = a1;
                         my[n] = sg;
                         if (NOISE) {
                             uint32_t *x = segx + (myrow * VS_MAXSEG + n) * VS_SEGX;
@@ -942,21 +948,19 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
             for (int r = 0; r < 4; r++) {
                 const int it = items[b + r];
                 const VsSeg sg = segs[it & 127];                          /* row*VS_MAXSEG + segment */
-                /* T2 >= 1: the row has open-phase samples.  A above 32767: x[T2] = (short)ceil(A) is negative,
-                 * the reference leaves the falling branch at once (:329) */
-                const int o1 = min(sg.a1, sg.Ad > 32767.0 ? sg.T2 : 2 * sg.T2);
-                const int i0 = sg.a0 + (it >> 7) * VS_ITEM_SAMPLES + lane; /* >= a0 >= 0 */
+                const int nn = (int)(sg.nr & 0xffffu), nrise = (int)(sg.nr >> 16);
+                const int k0 = (it >> 7) * VS_ITEM_SAMPLES + lane;
 #pragma unroll
                 for (int u = 0; u < VS_ITEM_SAMPLES / 32; u++) {
-                    const int i = i0 + 32 * u;
-                    const double tv = __ldg(sg.tab + min(i, 2 * sg.T2 - 1));
+                    const int k = k0 + 32 * u;
+                    const double tv = __ldg(sg.tab + k);                   /* past the segment: some other table entry, unused */
                     const double fall = __dadd_rn(__dsub_rn(__dmul_rn(sg.Kd, tv), sg.Kd), 1.0);
                     /* ceil as a 32-bit integer (host-side bounds keep it far from 2^31).  The reference tests the
                      * value after its (short) cast: above 32767 it wraps negative, i.e. below DC; on the falling
                      * branch the argument only decreases, so everything after the first value below DC is DC
                      * too -- also where the short would have wrapped back above DC */
-                    const int v = __double2int_ru(__dmul_rn(sg.Ad, i < sg.T2 ? tv : fall));
-                    if (i < o1 && v >= sg.DCi && v <= 32767) sg.out[i] = (int16_t)v;
+                    const int v = __double2int_ru(__dmul_rn(sg.Ad, k < nrise ? tv : fall));
+                    if (k < nn && v >= sg.DCi && v <= 32767) sg.out[k] = (int16_t)v;
                 }
             }
         }
@@ -984,21 +988,22 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
                         st = vs_rng_gen(st, lead + c1 + c2, lane, scratch);
                         __syncwarp();
                         const int32_t *d1 = scratch + lead - sg.a0, *d2 = scratch + lead + c1 - n2lo;
+                        int16_t *po = sg.out - sg.a0;                      /* the period's sample 0 */
                         /* two samples per lane and step: the chains (load, divide, scale, ceil, add, clip) are
                          * long and independent */
                         for (int i = sg.a0 + lane; i < n1hi; i += 64) {
                             const int i2 = i + 32;
                             const bool two = i2 < n1hi;
                             const int wa = vs_noise_w(d1[i], ndw), wb = vs_noise_w(d1[two ? i2 : i], ndw);
-                            sg.out[i] = (int16_t)vs_add_clip(sg.out[i], wa);
-                            if (two) sg.out[i2] = (int16_t)vs_add_clip(sg.out[i2], wb);
+                            po[i] = (int16_t)vs_add_clip(po[i], wa);
+                            if (two) po[i2] = (int16_t)vs_add_clip(po[i2], wb);
                         }
                         for (int i = n2lo + lane; i < sg.a1; i += 64) {
                             const int i2 = i + 32;
                             const bool two = i2 < sg.a1;
                             const int wa = vs_noise_w(d2[i], ndw), wb = vs_noise_w(d2[two ? i2 : i], ndw);
-                            sg.out[i] = (int16_t)vs_add_clip(sg.out[i], wa);
-                            if (two) sg.out[i2] = (int16_t)vs_add_clip(sg.out[i2], wb);
+                            po[i] = (int16_t)vs_add_clip(po[i], wa);
+                            if (two) po[i2] = (int16_t)vs_add_clip(po[i2], wb);
                         }
                         __syncwarp();
                     }
