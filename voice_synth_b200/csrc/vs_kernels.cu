@@ -11,7 +11,7 @@
  *
  *   vs_render_kernel     one row per (stream, time-chunk), 128 rows per CTA, no block-level
  *                        synchronisation.  Per 32 rows ONE consumer warp and FOUR producer warps share
- *                        two shared-memory tiles [32 rows][192 int16] through named barriers:
+ *                        two shared-memory tiles [32 rows][192 or 288 int16] through named barriers:
  *                          G  generate (producers): given the period table a sample is a pure function
  *                             of its index (flowgen_shimmer.c:319,328,335); lane-parallel bookkeeping
  *                             queues per-period segments, the open phases are evaluated as flat lists
@@ -779,7 +779,13 @@ __device__ __forceinline__ int vs_quant_fast_nocheck(double v)
 #define VS_NP        4
 #define VS_PW        4
 #define VS_MAXSEG    4                     /* period segments a row can queue per bookkeeping pass */
-#define VS_TILE_I16  (32 * VS_TS)
+/* Samples per row and window.  Every window costs a fixed amount on both sides (barrier, restart of the
+ * consumer's software pipeline, a bookkeeping pass, per-row loops, open phases cut in two), measured at
+ * ~22 % of the time with 192-sample windows; the fused non-noise kernels have the shared memory for 288.
+ * The noise variants (RNG states + scratch) and flow-only mode (two CTAs per SM) stay at 192. */
+__host__ __device__ constexpr int vs_win(int mode, bool noise) { return (mode != 0 /* VS_MODE_FLOW */ && !noise) ? VS_WIN_WIDE : VS_WIN; }
+#define VS_TS_OF(WIN)      ((WIN) + 2)          /* tile row stride in int16: an odd number of words => conflict-free columns */
+#define VS_TILE_I16_OF(WIN) (32 * VS_TS_OF(WIN))
 #define VS_THREADS_PAIRED ((VS_NP + VS_NP * VS_PW) * 32)
 /* flow mode: no consumer; the VS_PW warps of a group each do G then W for their own rows (one warp per 32
  * rows left the SM with 4-8 warps: 0.40 ms on the bench workload against 0.21 ms this way) */
@@ -799,14 +805,14 @@ struct __align__(16) VsSeg {
 #define VS_ITEM_SAMPLES 64                 /* open-phase samples per work item: two per lane */
 
 /* NTILE = tiles per group: 2 (double buffer) in the filtering modes, 1 in flow mode */
-#define VS_SMEM_TILES(NTILE) (VS_NP * (NTILE) * VS_TILE_I16 * 2)
+#define VS_SMEM_TILES(NTILE, WIN) (VS_NP * (NTILE) * VS_TILE_I16_OF(WIN) * 2)
 #define VS_SMEM_LANES (VS_NP * 32 * (int)sizeof(VsLane))
 #define VS_SMEM_SEGS  (VS_NP * 32 * VS_MAXSEG * (int)sizeof(VsSeg))
 #define VS_SEGX       3                                                /* noise words per segment: T3|T4, NoiseDistWidth, draws to skip */
 #define VS_SMEM_NSEG  (VS_NP * 32 * 4 + VS_NP * 32 * VS_MAXSEG * VS_SEGX * 4)   /* per-row segment counts + noise words */
 #define VS_ITEMS_BYTES (((32 * VS_MAXSEG * 4 + 4) * 2 + 15) & ~15)      /* work-item list of one producer warp */
 #define VS_SMEM_ITEMS(NPROD) (VS_NP * (NPROD) * VS_ITEMS_BYTES)
-#define VS_SMEM_BASE(NTILE) (VS_SMEM_TILES(NTILE) + VS_SMEM_LANES + VS_SMEM_SEGS + VS_SMEM_NSEG + VS_SMEM_ITEMS(VS_PW))
+#define VS_SMEM_BASE(NTILE, WIN) (VS_SMEM_TILES(NTILE, WIN) + VS_SMEM_LANES + VS_SMEM_SEGS + VS_SMEM_NSEG + VS_SMEM_ITEMS(VS_PW))
 /* noise: one RNG state per row, [NP][32 rows][32 words], oldest word first, and a
  * scratch of random() values per producer warp */
 #define VS_DRAW_SCRATCH 224                /* >= 7 rounds of 31 values >= VS_WIN */
@@ -831,6 +837,7 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
                                             int w, int lane, int row0, int step, const VsLane &mine, uint32_t &q,
                                             uint32_t *rngrow, int32_t *scratch)
 {
+    constexpr int WIN = vs_win(MODE, NOISE), TS = VS_TS_OF(WIN);
     const int myrow = row0 + lane * step;
     const bool have_row = myrow < 32;
     uint32_t *segx = reinterpret_cast<uint32_t *>(nsegs + 32);     /* [32][VS_MAXSEG][VS_SEGX] noise words per queued segment */
@@ -838,11 +845,11 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
     if (MODE == VS_MODE_FILTER) {
         for (int j = row0; j < 32; j += step) {
             const VsLane L = lanes[j];
-            const int wb = L.blk0 + w * VS_WIN;
+            const int wb = L.blk0 + w * WIN;
             if (wb >= L.hi) continue;
-            int16_t *trow = tile + j * VS_TS;
+            int16_t *trow = tile + j * TS;
 #pragma unroll
-            for (int k = lane; k < VS_WIN; k += 32) {
+            for (int k = lane; k < WIN; k += 32) {
                 const int m = wb + k;
                 trow[k] = (m >= L.nstart && m < L.hi) ? __ldg(L.fin + m) : (int16_t)0;
             }
@@ -852,18 +859,18 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
 
     /* 1. closed phase everywhere (:334-336), zeros outside the stream */
     for (int j = row0; j < 32; j += step) {
-        const int wb = lanes[j].blk0 + w * VS_WIN, hi = lanes[j].hi, ns = lanes[j].nstart;
+        const int wb = lanes[j].blk0 + w * WIN, hi = lanes[j].hi, ns = lanes[j].nstart;
         if (wb >= hi) continue;
-        int16_t *trow = tile + j * VS_TS;
+        int16_t *trow = tile + j * TS;
         const int dcs = lanes[j].DCs;
-        if (ns <= wb && wb + VS_WIN <= hi) {
+        if (ns <= wb && wb + WIN <= hi) {
             const uint32_t pat = (uint32_t)(uint16_t)dcs * 0x10001u;
             uint32_t *t32 = reinterpret_cast<uint32_t *>(trow);
 #pragma unroll
-            for (int k = lane; k < VS_WIN / 2; k += 32) t32[k] = pat;
+            for (int k = lane; k < WIN / 2; k += 32) t32[k] = pat;
         } else {
 #pragma unroll
-            for (int k = lane; k < VS_WIN; k += 32) {
+            for (int k = lane; k < WIN; k += 32) {
                 const int m = wb + k;
                 trow[k] = (m >= ns && m < hi) ? (int16_t)dcs : (int16_t)0;
             }
@@ -871,8 +878,8 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
     }
 
     /* 2. bookkeeping passes + cooperative evaluation */
-    const int wb_m = mine.blk0 + w * VS_WIN;
-    const int glo = max(wb_m, mine.nstart), ghi = min(wb_m + VS_WIN, mine.hi);
+    const int wb_m = mine.blk0 + w * WIN;
+    const int glo = max(wb_m, mine.nstart), ghi = min(wb_m + WIN, mine.hi);
     bool pending = have_row && wb_m < mine.hi;
     while (__any_sync(VS_FULL, pending)) {
         int n = 0, ngrp = 0;
@@ -893,8 +900,8 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
                     if (nopen > 0 || (NOISE && mine.noise)) {
                         VsSeg sg;
                         sg.Ad = e.Ad; sg.Kd = e.Kd; sg.tab = mine.ct + a0;
-                        sg.out = tile + myrow * VS_TS + (e.start - wb_m) + a0;
-                        sg.nr = (uint32_t)max(nopen, 0) | ((uint32_t)min(max(mine.T2 - a0, 0), VS_WIN) << 16);
+                        sg.out = tile + myrow * TS + (e.start - wb_m) + a0;
+                        sg.nr = (uint32_t)max(nopen, 0) | ((uint32_t)min(max(mine.T2 - a0, 0), WIN) << 16);
                         sg.DCi = mine.DCi;
                         sg.a0 = a0; sg.a1 = a1;
                         my[n] = sg;
@@ -1016,15 +1023,17 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
 }
 
 /* ---- W: one row, whole 16-byte pieces, consecutive lanes on consecutive pieces ----------------------- */
+template <int WIN>
 __device__ __forceinline__ void vs_write_row(const int16_t *trow, const VsLane &L, int w, int lane)
 {
     const int lo = L.lo, hi = L.hi;
-    const int wb = L.blk0 + w * VS_WIN;
-    if (wb >= hi || wb + VS_WIN <= lo) return;
-    if (lane < VS_WIN / 8) {
-        const int m0 = wb + 8 * lane;
+    const int wb = L.blk0 + w * WIN;
+    if (wb >= hi || wb + WIN <= lo) return;
+#pragma unroll
+    for (int pc = lane; pc < WIN / 8; pc += 32) {
+        const int m0 = wb + 8 * pc;
         if (m0 + 8 > lo && m0 < hi) {
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(trow) + lane * 4;
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(trow) + pc * 4;
             if (m0 >= lo && m0 + 8 <= hi) {
                 uint4 v;
                 v.x = src[0]; v.y = src[1]; v.z = src[2]; v.w = src[3];
@@ -1038,13 +1047,13 @@ __device__ __forceinline__ void vs_write_row(const int16_t *trow, const VsLane &
     }
 }
 
-/* ---- F: one lane, one row, VS_WIN samples of the order-22 recurrence, in place ---------------------- */
-template <bool EXACT, bool RAW, bool CHECKED>
+/* ---- F: one lane, one row, WIN samples of the order-22 recurrence, in place ---------------------- */
+template <int WIN, bool EXACT, bool RAW, bool CHECKED>
 __device__ __forceinline__ void vs_filter_window(uint32_t *row32, double (&y)[VS_RING], const double (&cf)[VS_RING],
                                                  double gaind, double pred, double *rrow, int wb, int lo, int hi)
 {
 #pragma unroll 1
-    for (int b = 0; b < VS_WIN / VS_RING; b++) {
+    for (int b = 0; b < WIN / VS_RING; b++) {
         uint32_t *blk32 = row32 + b * (VS_RING / 2);
 #pragma unroll
         for (int kk = 0; kk < VS_RING / 2; kk++) {
@@ -1090,13 +1099,14 @@ vs_render_kernel(const VsRenderArgs a)
     constexpr bool EXACT = (FLAGS & 1) != 0, RAW = (FLAGS & 2) != 0, CHECKED = (FLAGS & 4) != 0;
     extern __shared__ __align__(16) unsigned char s_raw[];
     constexpr int NTILE = PAIRED ? 2 : 1;
+    constexpr int WIN = vs_win(MODE, NOISE), TS = VS_TS_OF(WIN), TILE_I16 = VS_TILE_I16_OF(WIN);
     int16_t *s_tiles = reinterpret_cast<int16_t *>(s_raw);
-    VsLane *s_lanes = reinterpret_cast<VsLane *>(s_raw + VS_SMEM_TILES(NTILE));
-    VsSeg *s_segs = reinterpret_cast<VsSeg *>(s_raw + VS_SMEM_TILES(NTILE) + VS_SMEM_LANES);
-    int *s_nseg = reinterpret_cast<int *>(s_raw + VS_SMEM_TILES(NTILE) + VS_SMEM_LANES + VS_SMEM_SEGS);
-    unsigned char *s_items = s_raw + VS_SMEM_TILES(NTILE) + VS_SMEM_LANES + VS_SMEM_SEGS + VS_SMEM_NSEG;
-    uint32_t *s_rng = reinterpret_cast<uint32_t *>(s_raw + VS_SMEM_BASE(NTILE));
-    int32_t *s_scratch = reinterpret_cast<int32_t *>(s_raw + VS_SMEM_BASE(NTILE) + VS_NP * 32 * 32 * 4);
+    VsLane *s_lanes = reinterpret_cast<VsLane *>(s_raw + VS_SMEM_TILES(NTILE, WIN));
+    VsSeg *s_segs = reinterpret_cast<VsSeg *>(s_raw + VS_SMEM_TILES(NTILE, WIN) + VS_SMEM_LANES);
+    int *s_nseg = reinterpret_cast<int *>(s_raw + VS_SMEM_TILES(NTILE, WIN) + VS_SMEM_LANES + VS_SMEM_SEGS);
+    unsigned char *s_items = s_raw + VS_SMEM_TILES(NTILE, WIN) + VS_SMEM_LANES + VS_SMEM_SEGS + VS_SMEM_NSEG;
+    uint32_t *s_rng = reinterpret_cast<uint32_t *>(s_raw + VS_SMEM_BASE(NTILE, WIN));
+    int32_t *s_scratch = reinterpret_cast<int32_t *>(s_raw + VS_SMEM_BASE(NTILE, WIN) + VS_NP * 32 * 32 * 4);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int pair = warp % VS_NP;                       /* warps 0..NP-1 consume, NP.. produce */
@@ -1104,7 +1114,7 @@ vs_render_kernel(const VsRenderArgs a)
     const int prod = PAIRED ? warp / VS_NP - 1 : warp / VS_NP;   /* producer index inside the group, -1 = consumer */
     const bool consumer = PAIRED && warp < VS_NP;
     const int step = NPROD;                              /* a producer warp works rows prod, prod+step, ... */
-    int16_t *tile0 = s_tiles + pair * NTILE * VS_TILE_I16;
+    int16_t *tile0 = s_tiles + pair * NTILE * TILE_I16;
     VsLane *lanes = s_lanes + pair * 32;
     VsSeg *segs = s_segs + pair * 32 * VS_MAXSEG;
     int *nsegs = s_nseg + pair * (32 + 32 * VS_MAXSEG * VS_SEGX);
@@ -1157,7 +1167,7 @@ vs_render_kernel(const VsRenderArgs a)
         rrow = (RAW && a.raw_out) ? a.raw_out + st.out_off : nullptr;
     }
     /* windows to run: max over the 32 rows of the group (each warp of the group sees a subset) */
-    int nwin = active ? (me.hi - me.blk0 + VS_WIN - 1) / VS_WIN : 0;
+    int nwin = active ? (me.hi - me.blk0 + WIN - 1) / WIN : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nwin = max(nwin, __shfl_xor_sync(VS_FULL, nwin, o));
     if (!consumer && myrow < 32) lanes[myrow] = me;          /* producers publish the row descriptors */
@@ -1178,7 +1188,7 @@ vs_render_kernel(const VsRenderArgs a)
         for (int w = 0; w < nwin; w++) {
             vs_gen_tile<MODE, NOISE>(tile0, lanes, segs, nsegs, items, w, lane, prod, step, me, q, rngrow, scratch);
             __syncwarp();
-            for (int j = prod; j < 32; j += step) vs_write_row(tile0 + j * VS_TS, lanes[j], w, lane);
+            for (int j = prod; j < 32; j += step) vs_write_row<WIN>(tile0 + j * TS, lanes[j], w, lane);
             __syncwarp();
         }
         return;
@@ -1199,10 +1209,10 @@ vs_render_kernel(const VsRenderArgs a)
 
         vs_named_barrier(1 + pair, group_threads);           /* window 0 generated */
         for (int w = 0; w < nwin; w++) {
-            const int wb = me.blk0 + w * VS_WIN;
+            const int wb = me.blk0 + w * WIN;
             if (active && wb < me.hi)
-                vs_filter_window<EXACT, RAW, CHECKED>(
-                    reinterpret_cast<uint32_t *>(tile0 + (w & 1) * VS_TILE_I16 + lane * VS_TS), y, a.ncf, gaind, pred, rrow,
+                vs_filter_window<WIN, EXACT, RAW, CHECKED>(
+                    reinterpret_cast<uint32_t *>(tile0 + (w & 1) * TILE_I16 + lane * TS), y, a.ncf, gaind, pred, rrow,
                     wb, me.lo, me.hi);
             vs_named_barrier(1 + pair, group_threads);
         }
@@ -1210,17 +1220,17 @@ vs_render_kernel(const VsRenderArgs a)
         vs_gen_tile<MODE, NOISE>(tile0, lanes, segs, nsegs, items, 0, lane, prod, step, me, q, rngrow, scratch);
         vs_named_barrier(1 + pair, group_threads);           /* window 0 generated */
         for (int w = 0; w < nwin; w++) {
-            int16_t *other = tile0 + ((w + 1) & 1) * VS_TILE_I16;
+            int16_t *other = tile0 + ((w + 1) & 1) * TILE_I16;
             if (w > 0)
-                for (int j = prod; j < 32; j += step) vs_write_row(other + j * VS_TS, lanes[j], w - 1, lane);
+                for (int j = prod; j < 32; j += step) vs_write_row<WIN>(other + j * TS, lanes[j], w - 1, lane);
             if (w + 1 < nwin) {
                 vs_gen_tile<MODE, NOISE>(other, lanes, segs, nsegs, items, w + 1, lane, prod, step, me, q, rngrow, scratch);
             }
             vs_named_barrier(1 + pair, group_threads);
         }
         if (nwin > 0) {
-            const int16_t *last = tile0 + ((nwin - 1) & 1) * VS_TILE_I16;
-            for (int j = prod; j < 32; j += step) vs_write_row(last + j * VS_TS, lanes[j], nwin - 1, lane);
+            const int16_t *last = tile0 + ((nwin - 1) & 1) * TILE_I16;
+            for (int j = prod; j < 32; j += step) vs_write_row<WIN>(last + j * TS, lanes[j], nwin - 1, lane);
         }
     }
 }
@@ -1331,7 +1341,7 @@ template <int MODE, bool NOISE, int FLAGS>
 static void vs_go(const VsRenderArgs &a, cudaStream_t s)
 {
     const unsigned grid = a.n_rows / VS_NT;
-    const int dyn = VS_SMEM_BASE(MODE == VS_MODE_FLOW ? 1 : 2) + ((NOISE && MODE != VS_MODE_FILTER) ? VS_SMEM_NOISE : 0);
+    const int dyn = VS_SMEM_BASE(MODE == VS_MODE_FLOW ? 1 : 2, vs_win(MODE, NOISE)) + ((NOISE && MODE != VS_MODE_FILTER) ? VS_SMEM_NOISE : 0);
     cudaFuncSetAttribute(vs_render_kernel<MODE, NOISE, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     vs_render_kernel<MODE, NOISE, FLAGS><<<grid, VS_RENDER_THREADS(MODE), dyn, s>>>(a);
 }
