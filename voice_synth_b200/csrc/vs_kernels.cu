@@ -950,7 +950,19 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
         }
         __syncwarp();
 
-        for (int b = 0; b < total; b += 4) {
+        /* The table values of the NEXT four items are requested before the current four are worked out: the
+         * loads (L1 or L2, a few hundred cycles) then overlap the arithmetic instead of heading each step. */
+        double tvc[4][VS_ITEM_SAMPLES / 32], tvn[4][VS_ITEM_SAMPLES / 32];
+        auto fetch = [&](int b, double (&tv)[4][VS_ITEM_SAMPLES / 32]) {
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int it = items[b + r];
+                const double *tp = segs[it & 127].tab + ((it >> 7) * VS_ITEM_SAMPLES + lane);
+#pragma unroll
+                for (int u = 0; u < VS_ITEM_SAMPLES / 32; u++) tv[r][u] = __ldg(tp + 32 * u);   /* past the segment: some other table entry, unused */
+            }
+        };
+        auto work = [&](int b, const double (&tv)[4][VS_ITEM_SAMPLES / 32]) {
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 const int it = items[b + r];
@@ -960,15 +972,31 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
 #pragma unroll
                 for (int u = 0; u < VS_ITEM_SAMPLES / 32; u++) {
                     const int k = k0 + 32 * u;
-                    const double tv = __ldg(sg.tab + k);                   /* past the segment: some other table entry, unused */
-                    const double fall = __dadd_rn(__dsub_rn(__dmul_rn(sg.Kd, tv), sg.Kd), 1.0);
+                    const double fall = __dadd_rn(__dsub_rn(__dmul_rn(sg.Kd, tv[r][u]), sg.Kd), 1.0);
                     /* ceil as a 32-bit integer (host-side bounds keep it far from 2^31).  The reference tests the
                      * value after its (short) cast: above 32767 it wraps negative, i.e. below DC; on the falling
                      * branch the argument only decreases, so everything after the first value below DC is DC
                      * too -- also where the short would have wrapped back above DC */
-                    const int v = __double2int_ru(__dmul_rn(sg.Ad, k < nrise ? tv : fall));
+                    const int v = __double2int_ru(__dmul_rn(sg.Ad, k < nrise ? tv[r][u] : fall));
                     if (k < nn && v >= sg.DCi && v <= 32767) sg.out[k] = (int16_t)v;
                 }
+            }
+        };
+        if (MODE != VS_MODE_FLOW) {
+            if (total > 0) fetch(0, tvc);
+            for (int b = 0; b < total; b += 8) {
+                if (b + 4 < total) fetch(b + 4, tvn);
+                work(b, tvc);
+                if (b + 4 < total) {
+                    if (b + 8 < total) fetch(b + 8, tvc);
+                    work(b + 4, tvn);
+                }
+            }
+        } else {                                    /* flow-only mode: the registers of the second set would cost the
+                                                       second CTA per SM, which is worth more there */
+            for (int b = 0; b < total; b += 4) {
+                fetch(b, tvc);
+                work(b, tvc);
             }
         }
 
