@@ -784,8 +784,11 @@ __device__ __forceinline__ int vs_quant_fast_nocheck(double v)
  * ~22 % of the time with 192-sample windows; the fused non-noise kernels have the shared memory for 288.
  * The noise variants (RNG states + scratch) and flow-only mode (two CTAs per SM) stay at 192. */
 __host__ __device__ constexpr int vs_win(int mode, bool noise) { return (mode != 0 /* VS_MODE_FLOW */ && !noise) ? VS_WIN_WIDE : VS_WIN; }
-#define VS_TS_OF(WIN)      ((WIN) + 2)          /* tile row stride in int16: an odd number of words => conflict-free columns */
-#define VS_TILE_I16_OF(WIN) (32 * VS_TS_OF(WIN))
+/* tile row stride in int16.  With a consumer (lane = row walks down a column) an odd number of words keeps the
+ * columns conflict-free; flow-only mode has no column access, so its rows are 16-byte aligned instead and the
+ * fill and write-out phases move 16 bytes per lane */
+#define VS_TS_OF(MODE, WIN) ((MODE) == 0 /* VS_MODE_FLOW */ ? (WIN) + 8 : (WIN) + 2)
+#define VS_TILE_I16_OF(MODE, WIN) (32 * VS_TS_OF(MODE, WIN))
 #define VS_THREADS_PAIRED ((VS_NP + VS_NP * VS_PW) * 32)
 /* flow mode: no consumer; the VS_PW warps of a group each do G then W for their own rows (one warp per 32
  * rows left the SM with 4-8 warps: 0.40 ms on the bench workload against 0.21 ms this way) */
@@ -805,7 +808,7 @@ struct __align__(16) VsSeg {
 #define VS_ITEM_SAMPLES 64                 /* open-phase samples per work item: two per lane */
 
 /* NTILE = tiles per group: 2 (double buffer) in the filtering modes, 1 in flow mode */
-#define VS_SMEM_TILES(NTILE, WIN) (VS_NP * (NTILE) * VS_TILE_I16_OF(WIN) * 2)
+#define VS_SMEM_TILES(NTILE, WIN) (VS_NP * (NTILE) * VS_TILE_I16_OF((NTILE) == 1 ? 0 : 1, WIN) * 2)
 #define VS_SMEM_LANES (VS_NP * 32 * (int)sizeof(VsLane))
 #define VS_SMEM_SEGS  (VS_NP * 32 * VS_MAXSEG * (int)sizeof(VsSeg))
 #define VS_SEGX       3                                                /* noise words per segment: T3|T4, NoiseDistWidth, draws to skip */
@@ -837,7 +840,7 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
                                             int w, int lane, int row0, int step, const VsLane &mine, uint32_t &q,
                                             uint32_t *rngrow, int32_t *scratch)
 {
-    constexpr int WIN = vs_win(MODE, NOISE), TS = VS_TS_OF(WIN);
+    constexpr int WIN = vs_win(MODE, NOISE), TS = VS_TS_OF(MODE, WIN);
     const int myrow = row0 + lane * step;
     const bool have_row = myrow < 32;
     uint32_t *segx = reinterpret_cast<uint32_t *>(nsegs + 32);     /* [32][VS_MAXSEG][VS_SEGX] noise words per queued segment */
@@ -865,9 +868,15 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
         const int dcs = lanes[j].DCs;
         if (ns <= wb && wb + WIN <= hi) {
             const uint32_t pat = (uint32_t)(uint16_t)dcs * 0x10001u;
-            uint32_t *t32 = reinterpret_cast<uint32_t *>(trow);
+            if (MODE == VS_MODE_FLOW) {                                 /* 16-byte aligned rows */
+                uint4 *t128 = reinterpret_cast<uint4 *>(trow);
 #pragma unroll
-            for (int k = lane; k < WIN / 2; k += 32) t32[k] = pat;
+                for (int k = lane; k < WIN / 8; k += 32) t128[k] = make_uint4(pat, pat, pat, pat);
+            } else {
+                uint32_t *t32 = reinterpret_cast<uint32_t *>(trow);
+#pragma unroll
+                for (int k = lane; k < WIN / 2; k += 32) t32[k] = pat;
+            }
         } else {
 #pragma unroll
             for (int k = lane; k < WIN; k += 32) {
@@ -1051,7 +1060,7 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
 }
 
 /* ---- W: one row, whole 16-byte pieces, consecutive lanes on consecutive pieces ----------------------- */
-template <int WIN>
+template <int WIN, bool ALIGNED>
 __device__ __forceinline__ void vs_write_row(const int16_t *trow, const VsLane &L, int w, int lane)
 {
     const int lo = L.lo, hi = L.hi;
@@ -1064,7 +1073,8 @@ __device__ __forceinline__ void vs_write_row(const int16_t *trow, const VsLane &
             const uint32_t *src = reinterpret_cast<const uint32_t *>(trow) + pc * 4;
             if (m0 >= lo && m0 + 8 <= hi) {
                 uint4 v;
-                v.x = src[0]; v.y = src[1]; v.z = src[2]; v.w = src[3];
+                if (ALIGNED) v = *reinterpret_cast<const uint4 *>(src);
+                else { v.x = src[0]; v.y = src[1]; v.z = src[2]; v.w = src[3]; }
                 *reinterpret_cast<uint4 *>(L.orow + m0) = v;
             } else {
                 const int16_t *s16 = reinterpret_cast<const int16_t *>(src);
@@ -1127,7 +1137,7 @@ vs_render_kernel(const VsRenderArgs a)
     constexpr bool EXACT = (FLAGS & 1) != 0, RAW = (FLAGS & 2) != 0, CHECKED = (FLAGS & 4) != 0;
     extern __shared__ __align__(16) unsigned char s_raw[];
     constexpr int NTILE = PAIRED ? 2 : 1;
-    constexpr int WIN = vs_win(MODE, NOISE), TS = VS_TS_OF(WIN), TILE_I16 = VS_TILE_I16_OF(WIN);
+    constexpr int WIN = vs_win(MODE, NOISE), TS = VS_TS_OF(MODE, WIN), TILE_I16 = VS_TILE_I16_OF(MODE, WIN);
     int16_t *s_tiles = reinterpret_cast<int16_t *>(s_raw);
     VsLane *s_lanes = reinterpret_cast<VsLane *>(s_raw + VS_SMEM_TILES(NTILE, WIN));
     VsSeg *s_segs = reinterpret_cast<VsSeg *>(s_raw + VS_SMEM_TILES(NTILE, WIN) + VS_SMEM_LANES);
@@ -1216,7 +1226,7 @@ vs_render_kernel(const VsRenderArgs a)
         for (int w = 0; w < nwin; w++) {
             vs_gen_tile<MODE, NOISE>(tile0, lanes, segs, nsegs, items, w, lane, prod, step, me, q, rngrow, scratch);
             __syncwarp();
-            for (int j = prod; j < 32; j += step) vs_write_row<WIN>(tile0 + j * TS, lanes[j], w, lane);
+            for (int j = prod; j < 32; j += step) vs_write_row<WIN, MODE == VS_MODE_FLOW>(tile0 + j * TS, lanes[j], w, lane);
             __syncwarp();
         }
         return;
@@ -1250,7 +1260,7 @@ vs_render_kernel(const VsRenderArgs a)
         for (int w = 0; w < nwin; w++) {
             int16_t *other = tile0 + ((w + 1) & 1) * TILE_I16;
             if (w > 0)
-                for (int j = prod; j < 32; j += step) vs_write_row<WIN>(other + j * TS, lanes[j], w - 1, lane);
+                for (int j = prod; j < 32; j += step) vs_write_row<WIN, MODE == VS_MODE_FLOW>(other + j * TS, lanes[j], w - 1, lane);
             if (w + 1 < nwin) {
                 vs_gen_tile<MODE, NOISE>(other, lanes, segs, nsegs, items, w + 1, lane, prod, step, me, q, rngrow, scratch);
             }
@@ -1258,7 +1268,7 @@ vs_render_kernel(const VsRenderArgs a)
         }
         if (nwin > 0) {
             const int16_t *last = tile0 + ((nwin - 1) & 1) * TILE_I16;
-            for (int j = prod; j < 32; j += step) vs_write_row<WIN>(last + j * TS, lanes[j], nwin - 1, lane);
+            for (int j = prod; j < 32; j += step) vs_write_row<WIN, MODE == VS_MODE_FLOW>(last + j * TS, lanes[j], nwin - 1, lane);
         }
     }
 }
