@@ -232,3 +232,10 @@ def test_random_parameter_fuzz(ctx, vs, oracle):
             ctx.set_option(vs.OPT_PLAN_WARPS, -1)
             ctx.set_option(vs.OPT_CHUNK_SAMPLES, 0)
         _check_sample(oracle, vs, p, f, pcm, offs, ns, range(n), flow, foffs)
+    # a batch without any -z takes the pre-multiplied falling-branch tables (one per T2 and K): same streams alone
+    idx = np.flatnonzero(p.Kvar == 0)
+    assert 0.4 * n < idx.size < n
+    p0, f0 = p.select(idx), f.select(idx)
+    flow, foffs, ns = ctx.flowgen_batch(p0)
+    pcm, offs, _ = ctx.synth_batch(p0, f0)
+    _check_sample(oracle, vs, p0, f0, pcm, offs, ns, range(p0.n), flow, foffs)

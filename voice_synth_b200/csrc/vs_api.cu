@@ -95,6 +95,9 @@ struct vs_ctx {
     std::vector<double> cos_host;
     std::map<int, uint32_t> cos_index;
     std::vector<uint32_t> cos_fast;      /* T2 -> table offset, direct index in front of the map */
+    std::map<uint64_t, uint32_t> pulse_index;   /* (T2, bits of K) -> offset of the h / K*c-K+1 table */
+    uint64_t pulse_last_key = ~0ull;
+    uint32_t pulse_last_off = 0;
     int warm[VS_NUM_PRESETS];    /* warm-up samples per preset at opt_tol (gain-independent part) */
     double l1gain[VS_NUM_PRESETS]; /* sum |h[n]| of each preset: |y| <= l1gain * gain * max|x| */
     std::string err;
@@ -331,6 +334,38 @@ uint32_t cos_table_for(vs_ctx *ctx, int T2)
     return off;
 }
 
+/* Open-phase table of a stream whose closure speed never varies (-z absent: Knew == K in every period):
+ * h[0..T2) as above, then f[i] = (K*c[i] - K) + 1.0 with the reference's three roundings (:328), so that a
+ * falling-branch sample is ceil(A * f[i]) like a rising one is ceil(A * h[i]).  Saves the render kernel three of
+ * its five FP64 operations per open-phase sample. */
+uint32_t pulse_table_for(vs_ctx *ctx, int T2, float K)
+{
+    uint32_t kb;
+    memcpy(&kb, &K, 4);
+    const uint64_t key = ((uint64_t)(uint32_t)T2 << 32) | kb;
+    if (key == ctx->pulse_last_key) return ctx->pulse_last_off;
+    auto it = ctx->pulse_index.find(key);
+    uint32_t off;
+    if (it != ctx->pulse_index.end()) off = it->second;
+    else {
+        const uint32_t src = cos_table_for(ctx, T2);                  /* h then c; may grow cos_host */
+        off = (uint32_t)ctx->cos_host.size();
+        for (int i = 0; i < T2; i++) { const double h = ctx->cos_host[src + i]; ctx->cos_host.push_back(h); }
+        const double Kd = (double)K;
+        for (int i = 0; i < T2; i++) {
+            volatile double kc = Kd * ctx->cos_host[src + T2 + i];
+            volatile double d = kc - Kd;
+            volatile double f = d + 1.0;
+            const double fv = f;
+            ctx->cos_host.push_back(fv);
+        }
+        ctx->pulse_index[key] = off;
+    }
+    ctx->pulse_last_key = key;
+    ctx->pulse_last_off = off;
+    return off;
+}
+
 enum PtrKind { PK_HOST_PAGEABLE, PK_HOST_PINNED, PK_DEVICE };
 
 PtrKind classify(const void *p, int *dev_out)
@@ -481,7 +516,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
     /* ---- 1. per-stream descriptors ---------------------------------------------------------- */
     std::vector<VsStream> hs(n);
     uint64_t max_n = 0;
-    bool any_noise = false, checked_quant = false;
+    bool any_noise = false, checked_quant = false, any_kvar = false;
     for (size_t i = 0; i < n; i++) {
         VsStream &s = hs[i];
         memset(&s, 0, sizeof s);
@@ -498,6 +533,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             s.P = P;
             s.T2 = row_T2(r, s.P);
             s.cos_off = cos_table_for(ctx, s.T2);
+            any_kvar |= r.Kvar != 0.0f;
             s.amp = r.amp; s.DC = r.DC; s.jitter = r.jitter; s.shimmer = r.shimmer; s.K = r.K; s.Kvar = r.Kvar;
             s.noise = r.noise; s.seed = r.seed; s.flags = r.flags;
             s.DCs = (int16_t)(int32_t)r.DC;                            /* x[i] = par.DC (:321,:335) */
@@ -521,6 +557,8 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         hs[i].out_off = b.offsets ? b.offsets[i] : (uint64_t)i * max_n;
         if (b.mode == VS_MODE_FILTER) hs[i].in_off = b.in_offsets ? b.in_offsets[i] : (uint64_t)i * max_n;
         if (want_log) hs[i].log_off = b.log->rec_offsets[i];
+        /* the table the render kernel reads: with no -z anywhere in the batch, the falling branch pre-multiplied by K */
+        if (b.mode != VS_MODE_FILTER) hs[i].pulse_off = any_kvar ? hs[i].cos_off : pulse_table_for(ctx, hs[i].T2, hs[i].K);
     }
 
     prof.mark("stream descriptors");
@@ -894,6 +932,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             ra.pcm_out = d_pcm;
             ra.raw_out = d_raw;
             ra.checked_quant = checked_quant ? 1 : 0;
+            ra.general_pulse = any_kvar ? 1 : 0;
             ra.status = (int32_t *)sl.status[cp].p;
             /* one launch per vowel preset (its coefficients travel as kernel parameters); with more
              * than one preset the launches fork onto side streams so that they share the SMs */

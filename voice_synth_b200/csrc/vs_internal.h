@@ -41,7 +41,8 @@ struct VsStream {
     uint32_t chunk0;       /* id of the stream's first chunk                                      */
     uint32_t n_chunks;
     uint32_t tab_cap;      /* period-table capacity                                               */
-    uint32_t pad0;
+    uint32_t pulse_off;    /* first entry of the table the render kernel evaluates the open phase from: h[0..T2) then either
+                              c[0..T2) (== cos_off) or, for a stream whose closure speed never varies, K*c - K + 1           */
     uint64_t out_off;      /* samples, relative to pcm_out (and raw_out)                          */
     uint64_t in_off;       /* samples, relative to flow_in (filter-only mode)                     */
     uint64_t tab_off;      /* first entry of the stream's period table                            */
@@ -98,6 +99,8 @@ struct VsRenderArgs {
     int16_t        *pcm_out;
     double         *raw_out;        /* nullable                                                   */
     int             checked_quant;  /* 1: |waveform| may reach 2^30, use the range-checked quantiser */
+    int             general_pulse;  /* 1: some stream has -z Kvar > 0, its falling branch needs Knew of each period; 0: every
+                                       pulse_off table already holds K*c - K + 1, a sample is ceil(A * table[i])              */
     int32_t        *status;         /* device error flag (shared with the plan kernel)              */
 };
 

@@ -838,7 +838,7 @@ __device__ __forceinline__ void vs_named_barrier(int id, int count)
 template <int MODE, bool NOISE>
 __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, VsSeg *segs, int *nsegs, uint16_t *items,
                                             int w, int lane, int row0, int step, const VsLane &mine, uint32_t &q,
-                                            uint32_t *rngrow, int32_t *scratch)
+                                            uint32_t *rngrow, int32_t *scratch, bool general)
 {
     constexpr int WIN = vs_win(MODE, NOISE), TS = VS_TS_OF(MODE, WIN);
     const int myrow = row0 + lane * step;
@@ -981,12 +981,18 @@ __device__ __forceinline__ void vs_gen_tile(int16_t *tile, const VsLane *lanes, 
 #pragma unroll
                 for (int u = 0; u < VS_ITEM_SAMPLES / 32; u++) {
                     const int k = k0 + 32 * u;
-                    const double fall = __dadd_rn(__dsub_rn(__dmul_rn(sg.Kd, tv[r][u]), sg.Kd), 1.0);
+                    /* the factor A is multiplied with: h[i] while rising; on the falling branch (K*c - K) + 1 (:328),
+                     * which the table already holds unless some stream of the batch varies its closure speed */
+                    double fac = tv[r][u];
+                    if (general) {
+                        const double fall = __dadd_rn(__dsub_rn(__dmul_rn(sg.Kd, fac), sg.Kd), 1.0);
+                        fac = k < nrise ? fac : fall;
+                    }
                     /* ceil as a 32-bit integer (host-side bounds keep it far from 2^31).  The reference tests the
                      * value after its (short) cast: above 32767 it wraps negative, i.e. below DC; on the falling
                      * branch the argument only decreases, so everything after the first value below DC is DC
                      * too -- also where the short would have wrapped back above DC */
-                    const int v = __double2int_ru(__dmul_rn(sg.Ad, k < nrise ? tv[r][u] : fall));
+                    const int v = __double2int_ru(__dmul_rn(sg.Ad, fac));
                     if (k < nn && v >= sg.DCi && v <= 32767) sg.out[k] = (int16_t)v;
                 }
             }
@@ -1129,7 +1135,7 @@ __device__ __forceinline__ void vs_filter_window(uint32_t *row32, double (&y)[VS
 
 /* FLAGS: bit0 EXACT filter, bit1 RAW output, bit2 CHECKED quantiser */
 template <int MODE, bool NOISE, int FLAGS>
-__global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), 1)
+__global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), (MODE == VS_MODE_FLOW && !NOISE) ? 2 : 1)   /* flow-only: two CTAs per SM */
 vs_render_kernel(const VsRenderArgs a)
 {
     constexpr bool PAIRED = MODE != VS_MODE_FLOW;
@@ -1185,7 +1191,7 @@ vs_render_kernel(const VsRenderArgs a)
             me.nstart = (int)ck.gen_target;
         } else {
             me.tab = a.table + st.tab_off;
-            me.ct = a.costab + st.cos_off;
+            me.ct = a.costab + st.pulse_off;
             me.T2 = st.T2;
             me.DCi = (int)ceilf(st.DC);
             me.DCs = st.DCs;
@@ -1224,7 +1230,7 @@ vs_render_kernel(const VsRenderArgs a)
         /* ======== flow mode: every warp does G then W for its own rows ======== */
         __syncwarp();
         for (int w = 0; w < nwin; w++) {
-            vs_gen_tile<MODE, NOISE>(tile0, lanes, segs, nsegs, items, w, lane, prod, step, me, q, rngrow, scratch);
+            vs_gen_tile<MODE, NOISE>(tile0, lanes, segs, nsegs, items, w, lane, prod, step, me, q, rngrow, scratch, a.general_pulse != 0);
             __syncwarp();
             for (int j = prod; j < 32; j += step) vs_write_row<WIN, MODE == VS_MODE_FLOW>(tile0 + j * TS, lanes[j], w, lane);
             __syncwarp();
@@ -1255,14 +1261,14 @@ vs_render_kernel(const VsRenderArgs a)
             vs_named_barrier(1 + pair, group_threads);
         }
     } else {
-        vs_gen_tile<MODE, NOISE>(tile0, lanes, segs, nsegs, items, 0, lane, prod, step, me, q, rngrow, scratch);
+        vs_gen_tile<MODE, NOISE>(tile0, lanes, segs, nsegs, items, 0, lane, prod, step, me, q, rngrow, scratch, a.general_pulse != 0);
         vs_named_barrier(1 + pair, group_threads);           /* window 0 generated */
         for (int w = 0; w < nwin; w++) {
             int16_t *other = tile0 + ((w + 1) & 1) * TILE_I16;
             if (w > 0)
                 for (int j = prod; j < 32; j += step) vs_write_row<WIN, MODE == VS_MODE_FLOW>(other + j * TS, lanes[j], w - 1, lane);
             if (w + 1 < nwin) {
-                vs_gen_tile<MODE, NOISE>(other, lanes, segs, nsegs, items, w + 1, lane, prod, step, me, q, rngrow, scratch);
+                vs_gen_tile<MODE, NOISE>(other, lanes, segs, nsegs, items, w + 1, lane, prod, step, me, q, rngrow, scratch, a.general_pulse != 0);
             }
             vs_named_barrier(1 + pair, group_threads);
         }
