@@ -11,7 +11,7 @@
  *
  *   vs_render_kernel     one row per (stream, time-chunk), 128 rows per CTA, no block-level
  *                        synchronisation.  Per 32 rows ONE consumer warp and FOUR producer warps share
- *                        two shared-memory tiles [32 rows][192 or 288 int16] through named barriers:
+ *                        two shared-memory tiles [32 rows][192 or 240 int16] through named barriers:
  *                          G  generate (producers): given the period table a sample is a pure function
  *                             of its index (flowgen_shimmer.c:319,328,335); lane-parallel bookkeeping
  *                             queues per-period segments, the open phases are evaluated as flat lists
@@ -781,7 +781,8 @@ __device__ __forceinline__ int vs_quant_fast_nocheck(double v)
 #define VS_MAXSEG    4                     /* period segments a row can queue per bookkeeping pass */
 /* Samples per row and window.  Every window costs a fixed amount on both sides (barrier, restart of the
  * consumer's software pipeline, a bookkeeping pass, per-row loops, open phases cut in two), measured at
- * ~22 % of the time with 192-sample windows; the fused non-noise kernels have the shared memory for 288.
+ * ~22 % of the time with 192-sample windows; the fused non-noise kernels have the shared memory for more:
+ * 240 (30 16-byte pieces per row: one write-out step per row) measured as good as 288.
  * The noise variants (RNG states + scratch) and flow-only mode (two CTAs per SM) stay at 192. */
 __host__ __device__ constexpr int vs_win(int mode, bool noise) { return (mode != 0 /* VS_MODE_FLOW */ && !noise) ? VS_WIN_WIDE : VS_WIN; }
 /* tile row stride in int16.  With a consumer (lane = row walks down a column) an odd number of words keeps the
