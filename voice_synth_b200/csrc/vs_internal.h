@@ -21,8 +21,8 @@
 #define VS_NO_CHUNK 0xffffffffu
 #define VS_COS_SLACK 64         /* doubles readable past the last cosine table: a work item of the render kernel
                                   loads 64 table entries whatever the length of its segment (results discarded) */
-#define VS_WIN      192        /* samples per stream per render window (8 ring blocks, 24 x 16 B): noise variants, flow-only mode */
-#define VS_WIN_WIDE 240        /* the same for the fused / filter-only kernels without noise (10 ring blocks, 30 x 16 B: one
+#define VS_WIN      192        /* samples per stream per render window (8 ring blocks, 24 x 16 B): flow-only mode */
+#define VS_WIN_WIDE 240        /* the same for the fused / filter-only kernels (10 ring blocks, 30 x 16 B: one
                                   16-byte piece per lane in the write-out)                                                     */
 
 /* per-stream descriptor, prepared on the host, read once per thread */

@@ -781,10 +781,10 @@ __device__ __forceinline__ int vs_quant_fast_nocheck(double v)
 #define VS_MAXSEG    4                     /* period segments a row can queue per bookkeeping pass */
 /* Samples per row and window.  Every window costs a fixed amount on both sides (barrier, restart of the
  * consumer's software pipeline, a bookkeeping pass, per-row loops, open phases cut in two), measured at
- * ~22 % of the time with 192-sample windows; the fused non-noise kernels have the shared memory for more:
+ * ~22 % of the time with 192-sample windows; the fused kernels have the shared memory for more:
  * 240 (30 16-byte pieces per row: one write-out step per row) measured as good as 288.
- * The noise variants (RNG states + scratch) and flow-only mode (two CTAs per SM) stay at 192. */
-__host__ __device__ constexpr int vs_win(int mode, bool noise) { return (mode != 0 /* VS_MODE_FLOW */ && !noise) ? VS_WIN_WIDE : VS_WIN; }
+ * Flow-only mode (two CTAs per SM) stays at 192. */
+__host__ __device__ constexpr int vs_win(int mode, bool noise) { return mode != 0 /* VS_MODE_FLOW */ ? VS_WIN_WIDE : VS_WIN; }
 /* tile row stride in int16.  With a consumer (lane = row walks down a column) an odd number of words keeps the
  * columns conflict-free; flow-only mode has no column access, so its rows are 16-byte aligned instead and the
  * fill and write-out phases move 16 bytes per lane */
@@ -819,7 +819,7 @@ struct __align__(16) VsSeg {
 #define VS_SMEM_BASE(NTILE, WIN) (VS_SMEM_TILES(NTILE, WIN) + VS_SMEM_LANES + VS_SMEM_SEGS + VS_SMEM_NSEG + VS_SMEM_ITEMS(VS_PW))
 /* noise: one RNG state per row, [NP][32 rows][32 words], oldest word first, and a
  * scratch of random() values per producer warp */
-#define VS_DRAW_SCRATCH 224                /* >= 7 rounds of 31 values >= VS_WIN */
+#define VS_DRAW_SCRATCH 288                /* random() values of one period's share of a window (<= VS_WIN_WIDE) plus a few to skip */
 #define VS_SMEM_NOISE (VS_NP * 32 * 32 * 4 + VS_NP * VS_PW * VS_DRAW_SCRATCH * 4)
 
 __device__ __forceinline__ void vs_named_barrier(int id, int count)
