@@ -557,8 +557,18 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         hs[i].out_off = b.offsets ? b.offsets[i] : (uint64_t)i * max_n;
         if (b.mode == VS_MODE_FILTER) hs[i].in_off = b.in_offsets ? b.in_offsets[i] : (uint64_t)i * max_n;
         if (want_log) hs[i].log_off = b.log->rec_offsets[i];
-        /* the table the render kernel reads: with no -z anywhere in the batch, the falling branch pre-multiplied by K */
-        if (b.mode != VS_MODE_FILTER) hs[i].pulse_off = any_kvar ? hs[i].cos_off : pulse_table_for(ctx, hs[i].T2, hs[i].K);
+    }
+    /* the table the render kernel reads: with no -z anywhere in the batch, the falling branch pre-multiplied by K
+     * (one table per distinct (T2, K); a batch with a different K on every stream keeps the general path instead
+     * of growing the tables without bound) */
+    if (b.mode != VS_MODE_FILTER) {
+        for (size_t i = 0; i < n && !any_kvar; i++) {
+            const size_t before = ctx->cos_host.size();
+            hs[i].pulse_off = pulse_table_for(ctx, hs[i].T2, hs[i].K);
+            if (ctx->cos_host.size() > before && ctx->cos_host.size() > VS_PULSE_TABLE_CAP) any_kvar = true;
+        }
+        if (any_kvar)
+            for (size_t i = 0; i < n; i++) hs[i].pulse_off = hs[i].cos_off;
     }
 
     prof.mark("stream descriptors");

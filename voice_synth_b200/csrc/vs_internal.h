@@ -19,6 +19,7 @@
 #define VS_PLAN_WARP_MAX_NOISE 12288   /* some streams carry glottal noise */
 #define VS_RNG_DEG 31          /* glibc TYPE_3 */
 #define VS_NO_CHUNK 0xffffffffu
+#define VS_PULSE_TABLE_CAP (16u << 20)   /* doubles of cosine / pulse tables a context may accumulate (128 MB) */
 #define VS_COS_SLACK 64         /* doubles readable past the last cosine table: a work item of the render kernel
                                   loads 64 table entries whatever the length of its segment (results discarded) */
 #define VS_WIN      192        /* samples per stream per render window (8 ring blocks, 24 x 16 B): flow-only mode */
