@@ -7,8 +7,8 @@ NVFLAGS   := -O3 -std=c++17 $(ARCH) -lineinfo -fmad=false -cudart static \
 LIBDIR    := voice_synth_b200/lib
 LIB       := $(LIBDIR)/libvoicesynth_cuda.so
 CSRC      := voice_synth_b200/csrc
-SRCS      := $(CSRC)/vs_api.cu $(CSRC)/vs_kernels.cu
-HDRS      := include/voicesynth.h $(CSRC)/vs_internal.h $(CSRC)/vs_presets.h
+SRCS      := $(CSRC)/vs_api.cu $(CSRC)/vs_plan.cu $(CSRC)/vs_render.cu
+HDRS      := include/voicesynth.h $(CSRC)/vs_internal.h $(CSRC)/vs_presets.h $(CSRC)/vs_device.cuh
 
 all: lib host oracle
 
@@ -24,7 +24,7 @@ oracle:
 	$(MAKE) -C oracle all
 
 ptxas-info:
-	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o /dev/null $(CSRC)/vs_kernels.cu
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o /dev/null $(CSRC)/vs_render.cu
 
 clean:
 	rm -rf $(LIBDIR) host/bin oracle/_build

@@ -126,6 +126,9 @@ typedef struct vs_timing {
 #define VS_OPT_PLAN_WARPS      8  /* period-table kernel: 1 = one warp per stream, 0 = one thread per
                                      stream, -1 = auto: warps for small batches and glottal noise (-1)    */
 
+#define VS_OPT_SIMPLE_GEN      9  /* 1: render with the general (per-sample, branching) generator even where
+                                     the branch-free one applies -- for A/B checks (0)                    */
+
 /* ---- context -------------------------------------------------------------------------------- */
 int         vs_ctx_create(vs_ctx **out, const int *devices, int n_devices, uint32_t flags);
 void        vs_ctx_destroy(vs_ctx *ctx);

@@ -15,7 +15,7 @@ from ._lib import FilterParamsC, FlowParamsC, PeriodLogC, TimingC
 
 VS_F_JITTER, VS_F_SHIMMER, VS_F_NOISE = 1, 2, 4
 VS_OK, VS_EINVAL, VS_ERANGE, VS_EPRESET, VS_ENOMEM, VS_ECUDA, VS_ENODEV, VS_EOVERLAP = 0, -1, -2, -3, -4, -5, -6, -7
-OPT_CHUNK_SAMPLES, OPT_CARRY_TOL, OPT_EXACT_FILTER, OPT_SLAB_STREAMS, OPT_TARGET_WARPS, OPT_ASYNC_HOST, OPT_PLAN_WARPS = 1, 2, 3, 4, 5, 7, 8
+OPT_CHUNK_SAMPLES, OPT_CARRY_TOL, OPT_EXACT_FILTER, OPT_SLAB_STREAMS, OPT_TARGET_WARPS, OPT_ASYNC_HOST, OPT_PLAN_WARPS, OPT_SIMPLE_GEN = 1, 2, 3, 4, 5, 7, 8, 9
 
 PERIOD_DTYPE = np.dtype([("T", "<i4"), ("T2", "<i4"), ("T3", "<i4"), ("T4", "<i4"), ("A", "<f4"), ("Knew", "<f4"),
                          ("S", "<f4"), ("ndraws", "<i4"), ("ndw", "<i4"), ("x_pow", "<f4"), ("w_pow", "<f4"),

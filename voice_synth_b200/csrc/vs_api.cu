@@ -28,8 +28,12 @@
 #include "vs_presets.h"
 
 enum { VS_MODE_FLOW = 0, VS_MODE_SYNTH = 1, VS_MODE_FILTER = 2 };
+enum { VS_GEN_FAST = 0, VS_GEN_SIMPLE = 1 };
+enum { VS_FILT_INT = 0, VS_FILT_FMA = 1, VS_FILT_EXACT = 2 };
 cudaError_t vs_launch_plan(const VsPlanArgs &a, bool want_log, bool warp_per_stream, cudaStream_t s);
-cudaError_t vs_launch_render(const VsRenderArgs &a, int mode, bool noise, bool exact, cudaStream_t s);
+cudaError_t vs_launch_render(const VsRenderArgs &a, int mode, int gen, bool noise, int filt, cudaStream_t s);
+cudaError_t vs_render_init_device();
+int vs_render_window(int mode);
 cudaError_t vs_launch_fp64_peak(double *scratch, int blocks, int iters, cudaStream_t s);
 cudaError_t vs_launch_vnoise(int16_t *pcm, const VsNoiseRow *rows, uint32_t n_rows, cudaStream_t s);
 
@@ -60,8 +64,6 @@ struct Slot {
     unsigned call_parity = 0;
     cudaEvent_t slab_done[2] = {nullptr, nullptr};   /* D2H of the slab using pcm[k] finished */
     cudaEvent_t slab_ready = nullptr;                /* render of the current slab finished   */
-    cudaStream_t pstream[VS_NUM_PRESETS] = {};       /* one side stream per vowel preset: the per-preset   */
-    cudaEvent_t pfork = nullptr, pjoin[VS_NUM_PRESETS] = {};   /* render launches of a slab run concurrently */
     DevBuf streams[VS_DEPTH], chunks[VS_DEPTH], order[VS_DEPTH], table[VS_DEPTH], snap[VS_DEPTH], nper[VS_DEPTH], status[VS_DEPTH];
     DevBuf costab, coef, pcm[2], raw[2], flowin[2], log;
     PinBuf h_streams[VS_DEPTH], h_chunks[VS_DEPTH], h_order[VS_DEPTH], h_nper[VS_DEPTH], h_status[VS_DEPTH];
@@ -74,8 +76,11 @@ struct Slot {
     std::vector<uint64_t> plan_sig;
     std::vector<VsChunk> plan_chunks;
     std::vector<uint32_t> plan_order, plan_nch;
-    struct PlanGroup { size_t r0, r1; int preset; };
-    std::vector<std::vector<PlanGroup>> plan_groups;
+    struct PlanGeom {                                /* per slab: what the render launch needs besides the rows */
+        uint32_t cta_end[VS_NUM_PRESETS];
+        uint32_t cache_doubles;                      /* pulse-table cache a warp needs (fast generator)        */
+    };
+    std::vector<PlanGeom> plan_geom;
     std::vector<size_t> plan_slab_c0, plan_slab_r0;
     uint64_t plan_tab_total = 0, plan_warm_total = 0;
     uint64_t plan_version = 1, uploaded_version[VS_DEPTH] = {};        /* which plan the device copies of chunks/order hold (0 = none) */
@@ -92,6 +97,7 @@ struct vs_ctx {
     int opt_slab = 0;
     double opt_warps = 2.0;
     int opt_async_host = 0;
+    int opt_simple_gen = 0;      /* 1: never use the branch-free generator (debug / A-B) */
     std::vector<double> cos_host;
     std::map<int, uint32_t> cos_index;
     std::vector<uint32_t> cos_fast;      /* T2 -> table offset, direct index in front of the map */
@@ -221,7 +227,9 @@ int row_validate(const FlowRow &r, int *P_out = nullptr, uint64_t *n_out = nullp
     if (!(r.Kvar >= 0.0f && r.Kvar <= 1.0f)) return VS_ERANGE;        /* :530 */
     if (!(r.amp >= 0 && r.amp < 32767)) return VS_ERANGE;             /* :518 */
     if (!std::isfinite(r.DC) || !(r.DC >= 0.0f) || r.DC > 32767.0f) return VS_ERANGE;
-    if ((r.flags & VS_F_NOISE) && (!std::isfinite(r.noise) || !(r.noise > 0.0f))) return VS_ERANGE;
+    /* the tool accepts 0..50 dB, i.e. noise = 10^(dB/10) >= 1 (:505-511).  Below 0.1 (-10 dB) NoiseDistWidth could pass
+     * 2^19, the range the render kernel's two-operation noise sample is proven for (tests/tools/noisecheck.c) */
+    if ((r.flags & VS_F_NOISE) && (!std::isfinite(r.noise) || !(r.noise >= 0.1f))) return VS_ERANGE;
     if (r.flags & ~(VS_F_JITTER | VS_F_SHIMMER | VS_F_NOISE)) return VS_EINVAL;
     /* Falling branch (:327-332): x = (short)ceil(A*(K*c - K + 1)), left at the first x < DC.  Between two samples
      * the argument drops by at most A*K*2*sin(pi/(2*T2)); while that step stays below 2^15 the first value under DC
@@ -516,7 +524,9 @@ int run_batch(vs_ctx *ctx, const Batch &b)
     /* ---- 1. per-stream descriptors ---------------------------------------------------------- */
     std::vector<VsStream> hs(n);
     uint64_t max_n = 0;
-    bool any_noise = false, checked_quant = false, any_kvar = false;
+    bool any_noise = false, any_kvar = false;
+    bool int_filter = true;          /* every stream: integral gain, pre-emphasis 0 or 1 -> both commute to the integer input */
+    int t_min = 0x7fffffff, t_max = 0;   /* bounds on the pitch period lengths of the batch */
     for (size_t i = 0; i < n; i++) {
         VsStream &s = hs[i];
         memset(&s, 0, sizeof s);
@@ -539,6 +549,11 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             s.DCs = (int16_t)(int32_t)r.DC;                            /* x[i] = par.DC (:321,:335) */
             s.tab_cap = row_max_periods(r, s.n, s.P);
             any_noise |= (r.flags & VS_F_NOISE) != 0;
+            {   /* accepted periods satisfy 0.8*P <= T <= 1.2*P (flowgen_shimmer.c:290) */
+                const bool jit = (r.flags & VS_F_JITTER) && r.jitter != 0.0f;
+                t_min = std::min(t_min, jit ? std::max(1, (int)std::floor(0.8f * (float)P)) : P);
+                t_max = std::max(t_max, jit ? (int)std::ceil(1.2f * (float)P) + 1 : P);
+            }
         }
         if (b.mode != VS_MODE_FLOW) {
             const int key = b.ff && b.ff->preset ? b.ff->preset[i] : 'a';
@@ -548,8 +563,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             s.gain = b.ff && b.ff->gain ? b.ff->gain[i] : 10.0f;
             s.pre = b.ff && b.ff->pre ? b.ff->pre[i] : 1.0f;
             if (!std::isfinite(s.gain) || !std::isfinite(s.pre)) return fail(ctx, VS_ERANGE, "stream %zu: gain/pre not finite", i);
-            /* worst-case |waveform|: the unchecked quantiser needs it below 2^30 */
-            if (std::fabs((double)s.gain) * (1.0 + std::fabs((double)s.pre)) * 32768.0 * ctx->l1gain[pi] >= 536870912.0) checked_quant = true;
+            if (!(s.gain == std::floor(s.gain) && std::fabs(s.gain) <= 32767.0f && (s.pre == 0.0f || s.pre == 1.0f))) int_filter = false;
         }
         max_n = std::max<uint64_t>(max_n, s.n);
     }
@@ -601,6 +615,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
     memset(&ctx->timing, 0, sizeof ctx->timing);
     ctx->timing_pending = true;
     const bool exact = ctx->opt_exact != 0;
+    const bool compact = !(any_noise || any_kvar);           /* 8-byte period table entries (amplitude, length) suffice */
 
     /* ---- 4. per slot: descriptors up, then slabs of plan -> render -> copy ------------------- */
     for (size_t g = 0; g < nslots; g++) {
@@ -635,13 +650,15 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         /* chunk plan + row order: a function of the batch SHAPE only (lengths, presets, row phases,
          * options), so a call shaped like the previous one reuses it */
         std::vector<uint64_t> sig;
-        sig.reserve(ns + 8);
+        sig.reserve(3 * ns + 8);
         sig.push_back(((uint64_t)b.mode << 48) ^ ((uint64_t)n_slabs << 24) ^ (uint64_t)slab_streams);
         sig.push_back((uint64_t)(int64_t)ctx->opt_chunk ^ ((uint64_t)ctx->opt_exact << 62) ^ ((uint64_t)sl.sm_count << 40));
         { double t = ctx->opt_tol, w = ctx->opt_warps; uint64_t u; memcpy(&u, &t, 8); sig.push_back(u); memcpy(&u, &w, 8); sig.push_back(u); }
         for (size_t i = s0; i < s1; i++) {
             const uint64_t base_addr = out_dev ? (reinterpret_cast<uintptr_t>(b.pcm_out) >> 1) + hs[i].out_off : hs[i].out_off;
-            sig.push_back((uint64_t)hs[i].n | ((uint64_t)hs[i].preset << 32) | ((base_addr & 7) << 40) | ((uint64_t)(hs[i].tab_cap & 0xfffffu) << 44));
+            sig.push_back((uint64_t)hs[i].n | ((uint64_t)hs[i].preset << 32) | ((base_addr & 7) << 40));
+            sig.push_back((uint64_t)hs[i].tab_cap | ((uint64_t)hs[i].pulse_off << 32));          /* row order and table cache depend on these */
+            sig.push_back((uint64_t)(uint32_t)hs[i].T2);
         }
         const bool plan_hit = sig == sl.plan_sig;
         if (!plan_hit) {
@@ -705,34 +722,56 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         sl.plan_tab_total = tab_total;
         sl.plan_warm_total = warm_total;
         prof.mark("chunk plan");
-        /* render rows: inside each slab the chunks are grouped by vowel preset (one launch per preset:
-         * its coefficients are kernel parameters), longest first inside a preset (the 32 lanes of a
-         * warp then run a similar number of windows), and every preset group is padded to a whole CTA
-         * with VS_NO_CHUNK rows */
+        /* render rows: ONE launch per slab.  Rows are grouped by vowel preset and every preset group is padded to whole
+         * CTAs with VS_NO_CHUNK rows, so that a CTA's preset is a function of blockIdx (its coefficients then sit in
+         * uniform registers).  Inside a preset: longest first (the 32 lanes of a warp run a similar number of windows),
+         * rows of equal work next to each other by pulse table (a warp stages each distinct table of its rows once). */
         std::vector<uint32_t> &order = sl.plan_order;
         order.clear();
-        sl.plan_groups.assign(n_slabs, {});
+        sl.plan_geom.assign(n_slabs, Slot::PlanGeom());
         sl.plan_slab_r0.assign(n_slabs + 1, 0);
         for (size_t k = 0; k < n_slabs; k++) {
             sl.plan_slab_r0[k] = order.size();
             std::vector<uint32_t> ids(slab_c0[k + 1] - slab_c0[k]);
             for (size_t c = 0; c < ids.size(); c++) ids[c] = (uint32_t)(slab_c0[k] + c);
             auto preset_of = [&](uint32_t c) -> int { return b.mode == VS_MODE_FLOW ? 0 : hs[s0 + hc[c].stream].preset; };
-            std::stable_sort(ids.begin(), ids.end(), [&](uint32_t x, uint32_t y) {
+            std::sort(ids.begin(), ids.end(), [&](uint32_t x, uint32_t y) {
                 const int px = preset_of(x), py = preset_of(y);
                 if (px != py) return px < py;
-                return hc[x].emit_hi - hc[x].gen_target > hc[y].emit_hi - hc[y].gen_target;
+                const uint32_t wx = (hc[x].emit_hi - hc[x].gen_target) >> 6, wy = (hc[y].emit_hi - hc[y].gen_target) >> 6;
+                if (wx != wy) return wx > wy;
+                const uint32_t tx = hs[s0 + hc[x].stream].pulse_off, ty = hs[s0 + hc[y].stream].pulse_off;
+                if (tx != ty) return tx < ty;
+                return x < y;
             });
+            Slot::PlanGeom &gm = sl.plan_geom[k];
+            const size_t r_first = order.size();
             size_t i0 = 0;
+            int pr_done = 0;
             while (i0 < ids.size()) {
                 size_t i1 = i0;
                 const int pr = preset_of(ids[i0]);
                 while (i1 < ids.size() && preset_of(ids[i1]) == pr) i1++;
-                const size_t r0 = order.size();
+                for (; pr_done < pr; pr_done++) gm.cta_end[pr_done] = (uint32_t)((order.size() - r_first) / VS_NT);
                 for (size_t i = i0; i < i1; i++) order.push_back(ids[i]);
-                while (order.size() % VS_NT) order.push_back(VS_NO_CHUNK);
-                sl.plan_groups[k].push_back({r0, order.size(), pr});
+                while ((order.size() - r_first) % VS_NT) order.push_back(VS_NO_CHUNK);
                 i0 = i1;
+            }
+            for (; pr_done < VS_NUM_PRESETS; pr_done++) gm.cta_end[pr_done] = (uint32_t)((order.size() - r_first) / VS_NT);
+            /* pulse-table cache: the largest sum of distinct tables over the warps of the slab */
+            gm.cache_doubles = 0;
+            if (b.mode != VS_MODE_FILTER) {
+                for (size_t r = r_first; r < order.size(); r += 32) {
+                    uint32_t seen[32], nseen = 0, sum = 0;
+                    for (size_t j = r; j < r + 32; j++) {
+                        if (order[j] == VS_NO_CHUNK) continue;
+                        const VsStream &st = hs[s0 + hc[order[j]].stream];
+                        bool dup = false;
+                        for (uint32_t u = 0; u < nseen; u++) dup |= seen[u] == st.pulse_off;
+                        if (!dup) { seen[nseen++] = st.pulse_off; sum += 2u * (uint32_t)st.T2; }
+                    }
+                    gm.cache_doubles = std::max(gm.cache_doubles, sum);
+                }
             }
         }
         sl.plan_slab_r0[n_slabs] = order.size();
@@ -743,8 +782,6 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         const std::vector<VsChunk> &hc = sl.plan_chunks;
         const std::vector<uint32_t> &order = sl.plan_order;
         const std::vector<size_t> &slab_c0 = sl.plan_slab_c0, &slab_r0 = sl.plan_slab_r0;
-        const std::vector<std::vector<Slot::PlanGroup>> &slab_groups = sl.plan_groups;
-        typedef Slot::PlanGroup Group;
         const uint64_t tab_total = sl.plan_tab_total, warm_total = sl.plan_warm_total;
         {
             uint32_t c0acc = 0;
@@ -775,7 +812,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         if ((rc = dev_reserve(ctx, sl, sl.nper[cp], ns * sizeof(uint32_t)))) return rc;
         if ((rc = dev_reserve(ctx, sl, sl.status[cp], sizeof(int32_t)))) return rc;
         if (b.mode != VS_MODE_FILTER) {
-            if ((rc = dev_reserve(ctx, sl, sl.table[cp], (tab_total + 8) * sizeof(VsPeriod)))) return rc;
+            if ((rc = dev_reserve(ctx, sl, sl.table[cp], (tab_total + 8) * (compact ? sizeof(VsPeriodC) : sizeof(VsPeriod))))) return rc;
             if (any_noise && (rc = dev_reserve(ctx, sl, sl.snap[cp], nc * 32 * sizeof(uint32_t)))) return rc;
             if ((rc = dev_reserve(ctx, sl, sl.costab, (ctx->cos_host.size() + VS_COS_SLACK) * sizeof(double)))) return rc;
             if (sl.costab_uploaded != ctx->cos_host.size()) {
@@ -878,7 +915,8 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 pa.streams = (const VsStream *)sl.streams[cp].p + (a0 - s0);
                 pa.n_streams = (uint32_t)(a1 - a0);
                 pa.chunks = (VsChunk *)sl.chunks[cp].p;
-                pa.table = (VsPeriod *)sl.table[cp].p;
+                pa.table = sl.table[cp].p;
+                pa.compact = compact ? 1 : 0;
                 pa.rng_snap = any_noise ? (uint32_t *)sl.snap[cp].p : nullptr;
                 pa.n_periods = (uint32_t *)sl.nper[cp].p + (a0 - s0);
                 pa.costab = (const double *)sl.costab.p;
@@ -933,37 +971,41 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             memset(&ra, 0, sizeof ra);
             ra.streams = (const VsStream *)sl.streams[cp].p;
             ra.chunks = (const VsChunk *)sl.chunks[cp].p;
-            ra.n_chunks = (uint32_t)(c1 - c0);
-            ra.table = (const VsPeriod *)sl.table[cp].p;
+            ra.order = (const uint32_t *)sl.order[cp].p + slab_r0[k];
+            ra.n_rows = (uint32_t)(slab_r0[k + 1] - slab_r0[k]);
+            memcpy(ra.cta_end, sl.plan_geom[k].cta_end, sizeof ra.cta_end);
+            ra.table = sl.table[cp].p;
+            ra.compact = compact ? 1 : 0;
+            ra.n_periods = (const uint32_t *)sl.nper[cp].p;
             ra.rng_snap = any_noise ? (const uint32_t *)sl.snap[cp].p : nullptr;
             ra.costab = (const double *)sl.costab.p;
-            ra.coef = (const double *)sl.coef.p;
             ra.flow_in = d_in;
             ra.pcm_out = d_pcm;
             ra.raw_out = d_raw;
-            ra.checked_quant = checked_quant ? 1 : 0;
             ra.general_pulse = any_kvar ? 1 : 0;
             ra.status = (int32_t *)sl.status[cp].p;
-            /* one launch per vowel preset (its coefficients travel as kernel parameters); with more
-             * than one preset the launches fork onto side streams so that they share the SMs */
-            const std::vector<Group> &groups = slab_groups[k];
-            const bool fork = groups.size() > 1 && !getenv("VS_DEBUG_NOFORK");
-            if (fork) CU(cudaEventRecord(sl.pfork, sl.compute));
-            for (size_t gi = 0; gi < groups.size(); gi++) {
-                const Group &gr = groups[gi];
-                ra.order = (const uint32_t *)sl.order[cp].p + gr.r0;
-                ra.n_rows = (uint32_t)(gr.r1 - gr.r0);
-                for (int j = 0; j < VS_RING; j++) ra.ncf[j] = j <= VS_ORDER ? -vs_preset_den[gr.preset][j] : 0.0;
-                cudaStream_t st = fork ? sl.pstream[gi % VS_NUM_PRESETS] : sl.compute;
-                if (fork && gi < VS_NUM_PRESETS) CU(cudaStreamWaitEvent(st, sl.pfork, 0));
-                CU(vs_launch_render(ra, b.mode, any_noise, exact, st));
-                ctx->timing.launches++;
-            }
-            if (fork)
-                for (size_t gi = 0; gi < std::min<size_t>(groups.size(), VS_NUM_PRESETS); gi++) {
-                    CU(cudaEventRecord(sl.pjoin[gi], sl.pstream[gi]));
-                    CU(cudaStreamWaitEvent(sl.compute, sl.pjoin[gi], 0));
+            /* shared-memory geometry.  The fast generator keeps, per lane, a ring of upcoming period entries (filled
+             * one window ahead) and, per warp, the pulse tables of its rows; when the pitch periods of the batch are
+             * too short or the tables too many for that, the general generator takes over. */
+            const int win = vs_render_window(b.mode);
+            const uint32_t tile_bytes = 2u * 32u * (uint32_t)win * 2u;
+            int gen = VS_GEN_SIMPLE;
+            ra.warp_bytes = tile_bytes;
+            if (b.mode != VS_MODE_FILTER && compact && !ctx->opt_simple_gen && t_min >= 24 && t_max <= 8192) {
+                const uint32_t per_win = (uint32_t)(win / t_min) + 2u;      /* pitch periods a lane can start in one window */
+                const uint32_t ahead = 2u * per_win + 3u;
+                uint32_t R = 8;
+                while (R < ahead) R <<= 1;
+                const uint32_t cache = (sl.plan_geom[k].cache_doubles + 1u) & ~1u;
+                const uint32_t wbytes = tile_bytes + R * 256u + cache * 8u;
+                if (R <= 64 && 4u * wbytes <= (b.mode == VS_MODE_FLOW ? 72u : 200u) * 1024u) {
+                    gen = VS_GEN_FAST;
+                    ra.warp_bytes = wbytes; ra.ring_R = R; ra.ring_fetch = per_win + 2u; ra.ring_ahead = ahead; ra.cache_doubles = cache;
                 }
+            }
+            const int filt = exact ? VS_FILT_EXACT : ((int_filter && !b.raw_out) ? VS_FILT_INT : VS_FILT_FMA);
+            CU(vs_launch_render(ra, b.mode, gen, any_noise, filt, sl.compute));
+            ctx->timing.launches++;
             if (g == 0) { cudaEvent_t e2 = timing_event(sl); CU(cudaEventRecord(e2, sl.compute)); }
 
             if (!out_dev) {
@@ -1088,16 +1130,13 @@ int vs_ctx_create(vs_ctx **out, const int *devices, int n_devices, uint32_t flag
                   cudaEventCreateWithFlags(&s.slab_done[0], cudaEventDisableTiming) == cudaSuccess &&
                   cudaEventCreateWithFlags(&s.slab_done[1], cudaEventDisableTiming) == cudaSuccess &&
                   cudaEventCreateWithFlags(&s.slab_ready, cudaEventDisableTiming) == cudaSuccess &&
-                  cudaEventCreateWithFlags(&s.pfork, cudaEventDisableTiming) == cudaSuccess &&
+                  vs_render_init_device() == cudaSuccess &&
                   cudaMalloc(&s.coef.p, coef.size() * sizeof(double)) == cudaSuccess &&
                   cudaMemcpy(s.coef.p, coef.data(), coef.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
         s.coef.cap = coef.size() * sizeof(double);
         for (int k = 0; ok && k < VS_DEPTH; k++)
             ok = cudaEventCreateWithFlags(&s.call_done[k], cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&s.plan_done[k], cudaEventDisableTiming) == cudaSuccess;
-        for (int k = 0; ok && k < VS_NUM_PRESETS; k++)
-            ok = cudaStreamCreateWithFlags(&s.pstream[k], cudaStreamNonBlocking) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&s.pjoin[k], cudaEventDisableTiming) == cudaSuccess;
         ctx->slots.push_back(s);
         if (!ok) { cudaGetLastError(); vs_ctx_destroy(ctx); return VS_ECUDA; }
     }
@@ -1130,11 +1169,6 @@ void vs_ctx_destroy(vs_ctx *ctx)
         if (s.slab_done[0]) cudaEventDestroy(s.slab_done[0]);
         if (s.slab_done[1]) cudaEventDestroy(s.slab_done[1]);
         if (s.slab_ready) cudaEventDestroy(s.slab_ready);
-        if (s.pfork) cudaEventDestroy(s.pfork);
-        for (int k = 0; k < VS_NUM_PRESETS; k++) {
-            if (s.pjoin[k]) cudaEventDestroy(s.pjoin[k]);
-            if (s.pstream[k]) cudaStreamDestroy(s.pstream[k]);
-        }
         if (s.copy) cudaStreamDestroy(s.copy);
         if (s.compute && s.own_compute) cudaStreamDestroy(s.compute);
     }
@@ -1155,6 +1189,7 @@ int vs_ctx_set_option(vs_ctx *ctx, int option, double value)
     case VS_OPT_TARGET_WARPS: if (!(value > 0)) return VS_EINVAL; ctx->opt_warps = value; return VS_OK;
     case VS_OPT_ASYNC_HOST: ctx->opt_async_host = value != 0.0; return VS_OK;
     case VS_OPT_PLAN_WARPS: ctx->opt_plan_warps = value < 0 ? -1 : (value != 0.0); return VS_OK;
+    case VS_OPT_SIMPLE_GEN: ctx->opt_simple_gen = value != 0.0; return VS_OK;
     default: return VS_EINVAL;
     }
 }

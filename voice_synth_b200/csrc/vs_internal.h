@@ -4,6 +4,7 @@
 #define VS_INTERNAL_H
 #include <stdint.h>
 
+#define VS_NUM_PRESETS_I 10   /* == VS_NUM_PRESETS (vs_presets.h) */
 #define VS_ORDER   22          /* vowel_new.c:172 */
 #define VS_RING    24          /* state ring / samples per unrolled filter block (>= VS_ORDER, 3 x 16 B of PCM) */
 #define VS_NT      128         /* rows per CTA of the render kernel (and its RNG stride)           */
@@ -20,11 +21,13 @@
 #define VS_RNG_DEG 31          /* glibc TYPE_3 */
 #define VS_NO_CHUNK 0xffffffffu
 #define VS_PULSE_TABLE_CAP (16u << 20)   /* doubles of cosine / pulse tables a context may accumulate (128 MB) */
-#define VS_COS_SLACK 64         /* doubles readable past the last cosine table: a work item of the render kernel
-                                  loads 64 table entries whatever the length of its segment (results discarded) */
-#define VS_WIN      192        /* samples per stream per render window (8 ring blocks, 24 x 16 B): flow-only mode */
-#define VS_WIN_WIDE 240        /* the same for the fused / filter-only kernels (10 ring blocks, 30 x 16 B: one
-                                  16-byte piece per lane in the write-out)                                                     */
+#define VS_COS_SLACK 64         /* doubles allocated past the last cosine table */
+/* samples per row and render window (vs_render.cu): multiples of the 24-sample filter ring with an ODD number of
+ * ring blocks, so that the tile row stride (2*WIN bytes) is 16 x odd -- every lane's 16-byte stores down its own
+ * row are bank-conflict free and every row is a legal source of a bulk (TMA) store */
+#define VS_WIN_SYNTH  216
+#define VS_WIN_FLOW   120
+#define VS_WIN_FILTER 120
 
 /* per-stream descriptor, prepared on the host, read once per thread */
 struct VsStream {
@@ -56,8 +59,9 @@ struct VsChunk {
     uint32_t stream;
     uint32_t emit_lo, emit_hi;   /* samples [emit_lo, emit_hi) are written by this chunk           */
     uint32_t gen_target;         /* generation starts at the period containing this sample         */
-    uint32_t first_period;       /* filled by the plan kernel                                      */
-    uint32_t pad[3];
+    uint32_t first_period;       /* filled by the plan kernel: the period containing gen_target    */
+    uint32_t first_start;        /* filled by the plan kernel: first sample of that period         */
+    uint32_t pad[2];
 };
 
 /* period table entry (32 B) written by the plan kernel, read by the render kernel */
@@ -71,12 +75,19 @@ struct VsPeriod {
     int32_t  ndw;          /* NoiseDistWidth                                                      */
 };
 
+/* compact period table entry (8 B): all a batch without glottal noise and without -z needs */
+struct VsPeriodC {
+    float    A;            /* Amplitude                                                           */
+    uint32_t T;            /* period length                                                       */
+};
+
 /* kernel launch argument blocks */
 struct VsPlanArgs {
     const VsStream *streams;
     uint32_t        n_streams;
     VsChunk        *chunks;
-    VsPeriod       *table;
+    void           *table;          /* VsPeriod[] or, when compact, VsPeriodC[]                   */
+    int             compact;
     uint32_t       *rng_snap;       /* [n_chunks][32] or NULL                                     */
     uint32_t       *n_periods;      /* [n_streams]                                                */
     const double   *costab;
@@ -89,21 +100,27 @@ struct VsRenderArgs {
     const VsStream *streams;
     const VsChunk  *chunks;
     const uint32_t *order;          /* render row t works on chunk order[t]; VS_NO_CHUNK = padding   */
-    double          ncf[VS_RING];   /* -A[j] of the ONE vowel preset this launch serves: as kernel
-                                       parameters they are constant-bank immediates of the DFMAs   */
+    uint32_t        cta_end[VS_NUM_PRESETS_I];   /* CTAs [cta_end[p-1], cta_end[p]) serve vowel preset p: the preset is a
+                                       function of blockIdx and kernel parameters only, so the coefficients are
+                                       read into UNIFORM registers (DFMA R, R, UR, R)                 */
     uint32_t        n_rows;         /* rows incl. padding, multiple of VS_NT                         */
-    uint32_t        n_chunks;
-    const VsPeriod *table;
+    const void     *table;          /* VsPeriod[] or VsPeriodC[] (compact)                           */
+    int             compact;
+    const uint32_t *n_periods;      /* [n_streams] periods the plan kernel wrote                     */
     const uint32_t *rng_snap;
     const double   *costab;
-    const double   *coef;           /* [10][24] denominators, device copy                         */
     const int16_t  *flow_in;        /* filter-only mode                                           */
     int16_t        *pcm_out;
     double         *raw_out;        /* nullable                                                   */
-    int             checked_quant;  /* 1: |waveform| may reach 2^30, use the range-checked quantiser */
     int             general_pulse;  /* 1: some stream has -z Kvar > 0, its falling branch needs Knew of each period; 0: every
                                        pulse_off table already holds K*c - K + 1, a sample is ceil(A * table[i])              */
     int32_t        *status;         /* device error flag (shared with the plan kernel)              */
+    /* shared-memory geometry chosen by the host (vs_api.cu, render_geometry) */
+    uint32_t        warp_bytes;     /* per-warp region: 2 tiles | period ring | pulse-table cache    */
+    uint32_t        ring_R;         /* period-ring entries per lane (power of two)                   */
+    uint32_t        ring_fetch;     /* entries a lane may fetch per window                           */
+    uint32_t        ring_ahead;     /* how far beyond the current period the ring is kept filled     */
+    uint32_t        cache_doubles;  /* pulse-table cache per warp                                    */
 };
 
 /* vowel -n (N1): one entry per stream */
