@@ -34,6 +34,7 @@ cudaError_t vs_launch_plan(const VsPlanArgs &a, bool want_log, bool warp_per_str
 cudaError_t vs_launch_render(const VsRenderArgs &a, int mode, int gen, bool noise, int filt, cudaStream_t s);
 cudaError_t vs_render_init_device();
 int vs_render_window(int mode);
+int vs_render_tiles(int mode);
 cudaError_t vs_launch_fp64_peak(double *scratch, int blocks, int iters, cudaStream_t s);
 cudaError_t vs_launch_vnoise(int16_t *pcm, const VsNoiseRow *rows, uint32_t n_rows, cudaStream_t s);
 
@@ -527,6 +528,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
     bool any_noise = false, any_kvar = false;
     bool int_filter = true;          /* every stream: integral gain, pre-emphasis 0 or 1 -> both commute to the integer input */
     int t_min = 0x7fffffff, t_max = 0;   /* bounds on the pitch period lengths of the batch */
+    bool amp_fits = true;            /* no amplitude can pass 32767 (fast generator) */
     for (size_t i = 0; i < n; i++) {
         VsStream &s = hs[i];
         memset(&s, 0, sizeof s);
@@ -552,7 +554,10 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             {   /* accepted periods satisfy 0.8*P <= T <= 1.2*P (flowgen_shimmer.c:290) */
                 const bool jit = (r.flags & VS_F_JITTER) && r.jitter != 0.0f;
                 t_min = std::min(t_min, jit ? std::max(1, (int)std::floor(0.8f * (float)P)) : P);
-                t_max = std::max(t_max, jit ? (int)std::ceil(1.2f * (float)P) + 1 : P);
+                const int tm = jit ? (int)std::ceil(1.2f * (float)P) + 1 : P;
+                t_max = std::max(t_max, tm);
+                s.tpad = (uint32_t)((tm + 9) & ~1);                     /* refined per table below */
+                if ((r.flags & VS_F_SHIMMER) && r.shimmer != 0.0f ? 1.8f * (float)r.amp > 32767.0f : r.amp > 32767) amp_fits = false;
             }
         }
         if (b.mode != VS_MODE_FLOW) {
@@ -583,6 +588,10 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         }
         if (any_kvar)
             for (size_t i = 0; i < n; i++) hs[i].pulse_off = hs[i].cos_off;
+        /* streams that share a table share its padded length */
+        std::map<uint32_t, uint32_t> pad;
+        for (size_t i = 0; i < n; i++) { uint32_t &v = pad[hs[i].pulse_off]; v = std::max(v, hs[i].tpad); }
+        for (size_t i = 0; i < n; i++) hs[i].tpad = pad[hs[i].pulse_off];
     }
 
     prof.mark("stream descriptors");
@@ -658,7 +667,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             const uint64_t base_addr = out_dev ? (reinterpret_cast<uintptr_t>(b.pcm_out) >> 1) + hs[i].out_off : hs[i].out_off;
             sig.push_back((uint64_t)hs[i].n | ((uint64_t)hs[i].preset << 32) | ((base_addr & 7) << 40));
             sig.push_back((uint64_t)hs[i].tab_cap | ((uint64_t)hs[i].pulse_off << 32));          /* row order and table cache depend on these */
-            sig.push_back((uint64_t)(uint32_t)hs[i].T2);
+            sig.push_back((uint64_t)(uint32_t)hs[i].T2 | ((uint64_t)hs[i].tpad << 32));
         }
         const bool plan_hit = sig == sl.plan_sig;
         if (!plan_hit) {
@@ -768,7 +777,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                         const VsStream &st = hs[s0 + hc[order[j]].stream];
                         bool dup = false;
                         for (uint32_t u = 0; u < nseen; u++) dup |= seen[u] == st.pulse_off;
-                        if (!dup) { seen[nseen++] = st.pulse_off; sum += 2u * (uint32_t)st.T2; }
+                        if (!dup) { seen[nseen++] = st.pulse_off; sum += st.tpad; }
                     }
                     gm.cache_doubles = std::max(gm.cache_doubles, sum);
                 }
@@ -988,10 +997,10 @@ int run_batch(vs_ctx *ctx, const Batch &b)
              * one window ahead) and, per warp, the pulse tables of its rows; when the pitch periods of the batch are
              * too short or the tables too many for that, the general generator takes over. */
             const int win = vs_render_window(b.mode);
-            const uint32_t tile_bytes = 2u * 32u * (uint32_t)win * 2u;
+            const uint32_t tile_bytes = (uint32_t)vs_render_tiles(b.mode) * 32u * (uint32_t)win * 2u;
             int gen = VS_GEN_SIMPLE;
-            ra.warp_bytes = tile_bytes;
-            if (b.mode != VS_MODE_FILTER && compact && !ctx->opt_simple_gen && t_min >= 24 && t_max <= 8192) {
+            ra.warp_bytes = tile_bytes + (b.mode == VS_MODE_FILTER ? 32u * 16u : 0u);      /* filter-only: row descriptors of the loader */
+            if (b.mode != VS_MODE_FILTER && compact && amp_fits && !ctx->opt_simple_gen && t_min >= 24 && t_max <= 8192) {
                 const uint32_t per_win = (uint32_t)(win / t_min) + 2u;      /* pitch periods a lane can start in one window */
                 const uint32_t ahead = 2u * per_win + 3u;
                 uint32_t R = 8;

@@ -25,7 +25,7 @@
 /* samples per row and render window (vs_render.cu): multiples of the 24-sample filter ring with an ODD number of
  * ring blocks, so that the tile row stride (2*WIN bytes) is 16 x odd -- every lane's 16-byte stores down its own
  * row are bank-conflict free and every row is a legal source of a bulk (TMA) store */
-#define VS_WIN_SYNTH  216
+#define VS_WIN_SYNTH  168
 #define VS_WIN_FLOW   120
 #define VS_WIN_FILTER 120
 
@@ -48,6 +48,8 @@ struct VsStream {
     uint32_t tab_cap;      /* period-table capacity                                               */
     uint32_t pulse_off;    /* first entry of the table the render kernel evaluates the open phase from: h[0..T2) then either
                               c[0..T2) (== cos_off) or, for a stream whose closure speed never varies, K*c - K + 1           */
+    uint32_t tpad;         /* entries of that table's zero-padded copy in shared memory (fast generator): above the longest
+                              pitch period of any stream that uses the table                                                 */
     uint64_t out_off;      /* samples, relative to pcm_out (and raw_out)                          */
     uint64_t in_off;       /* samples, relative to flow_in (filter-only mode)                     */
     uint64_t tab_off;      /* first entry of the stream's period table                            */

@@ -65,16 +65,36 @@ __device__ __forceinline__ int vs_noise_w2(int32_t r, double ndwd)
     return vs_ceil_s16(__dmul_rn(t, ndwd));
 }
 
-template <int MODE, int GEN, bool NOISE, int FILT, bool RAW>
-__global__ void __launch_bounds__(VS_NT, MODE == VS_MODE_FLOW ? 3 : 1) vs_render_kernel(const VsRenderArgs a)
+__device__ __forceinline__ void vs_pair_barrier(int pair)
 {
-    constexpr int WIN = vs_win(MODE), TSB = WIN * 2, TILE = 32 * TSB;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
+}
+
+/* what the loader warp of the filter-only mode needs to know about a row */
+struct __align__(16) VsRowIn {
+    const int16_t *fin;
+    int32_t nstart, hi;
+};
+
+#define VS_RENDER_THREADS(MODE) ((MODE) == VS_MODE_FLOW ? VS_NT : 2 * VS_NT)
+#define VS_RENDER_TILES(MODE)   ((MODE) == VS_MODE_FLOW ? 2 : 3)
+
+template <int MODE, int GEN, bool NOISE, int FILT, bool RAW>
+__global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW ? 3 : 1) vs_render_kernel(const VsRenderArgs a)
+{
+    constexpr int WIN = vs_win(MODE), TSB = WIN * 2, TILE = 32 * TSB, NGRP = WIN / VS_GROUP;
+    constexpr int NT = VS_RENDER_TILES(MODE);
     constexpr bool HASGEN = MODE != VS_MODE_FILTER, HASFILT = MODE != VS_MODE_FLOW;
     constexpr bool FAST = HASGEN && GEN == VS_GEN_FAST;
     static_assert((WIN % VS_RING) == 0 && ((WIN / VS_RING) & 1) == 1, "window = odd number of ring blocks");
     static_assert(!(FAST && NOISE), "the fast generator has no noise path");
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    /* Roles.  Rows come in groups of 32 ("pairs"); pair p of a CTA is served by warp p, the FILTER warp (F), and
+     * warp p+4, the GENERATOR warp (G): both sit on SM sub-partition p, where F keeps the FP64 pipe busy and G's
+     * integer work fills the issue slots in between.  Flow-only mode has G warps alone. */
+    const int pair = warp & 3;
+    const bool is_f = HASFILT && warp < 4;
 
     /* vowel preset of this CTA: uniform by construction */
     int preset = 0;
@@ -83,54 +103,36 @@ __global__ void __launch_bounds__(VS_NT, MODE == VS_MODE_FLOW ? 3 : 1) vs_render
         for (int p = 0; p < VS_NUM_PRESETS - 1; p++) preset += blockIdx.x >= a.cta_end[p] ? 1 : 0;
     }
 
-    /* shared memory: per warp [tile 0 | tile 1 | period ring | pulse-table cache], then the CTA's RNG states */
-    const uint32_t tile_off = (uint32_t)warp * a.warp_bytes;
-    const uint32_t ring_off = tile_off + 2u * TILE;
+    /* shared memory: per pair [NT tiles | period ring | pulse-table cache | row descriptors], then the CTA's RNG states */
+    const uint32_t tile_off = (uint32_t)pair * a.warp_bytes;
+    const uint32_t ring_off = tile_off + (uint32_t)NT * TILE;
     const uint32_t cache_off = ring_off + a.ring_R * 256u;
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
     uint32_t *s_rng = reinterpret_cast<uint32_t *>(smem + 4u * a.warp_bytes);      /* [31][VS_NT], NOISE only */
 
-    /* ---- the lane's row ------------------------------------------------------------------------------- */
-    const uint32_t t = blockIdx.x * VS_NT + threadIdx.x;
+    /* ---- the lane's row (lane l of F and lane l of G serve the same row) -------------------------------- */
+    const uint32_t t = blockIdx.x * VS_NT + (uint32_t)pair * 32u + (uint32_t)lane;
     const uint32_t chunk_id = t < a.n_rows ? __ldg(a.order + t) : VS_NO_CHUNK;
-    const bool active = chunk_id != VS_NO_CHUNK;
+    bool active = chunk_id != VS_NO_CHUNK;
     int lo = 0, hi = 0, nstart = 0;
+    uint32_t stream_id = 0, q0u = 0;
     int16_t *orow = nullptr;
-    const int16_t *fin = nullptr;
-    double *rrow = nullptr;
-    double gaind = 0.0, pred = 0.0;
-    int gain_i = 0, pre_i = 0;
-    int T2 = 0, DCi = 0, DCs = 0, q0 = 0, nper = 0;
-    uint32_t pulse_off = 0xffffffffu;
-    bool nz = false;
-    const unsigned char *ptab = nullptr;                    /* the row's period table */
     if (active) {
         const VsChunk ck = a.chunks[chunk_id];
-        const VsStream *st = a.streams + ck.stream;
-        orow = a.pcm_out + st->out_off;
+        stream_id = ck.stream;
+        orow = a.pcm_out + a.streams[stream_id].out_off;
         lo = (int)ck.emit_lo; hi = (int)ck.emit_hi;
-        gaind = (double)st->gain; pred = (double)st->pre;
-        gain_i = (int)st->gain; pre_i = (int)st->pre;
-        rrow = (RAW && a.raw_out) ? a.raw_out + st->out_off : nullptr;
-        if (MODE == VS_MODE_FILTER) {
-            fin = a.flow_in + st->in_off;
-            nstart = (int)ck.gen_target;
-        } else {
-            ptab = reinterpret_cast<const unsigned char *>(a.table) + st->tab_off * (a.compact ? sizeof(VsPeriodC) : sizeof(VsPeriod));
-            T2 = st->T2;
-            DCi = (int)ceilf(st->DC);                       /* (float)x < DC  <=>  x < ceil(DC) for integer x */
-            DCs = st->DCs;
-            nz = (st->flags & VS_F_NOISE) != 0;
-            pulse_off = st->pulse_off;
-            q0 = (int)ck.first_period;
-            nper = (int)__ldg(a.n_periods + ck.stream);
-            nstart = (int)ck.first_start;
-            if (q0 >= nper || q0 >= (int)st->tab_cap) {     /* the plan kernel did not reach this chunk: refuse to walk garbage */
-                atomicExch(a.status, VS_ECUDA);
-                nper = 0; hi = 0; lo = 0; nstart = 0;
+        q0u = ck.first_period;
+        nstart = MODE == VS_MODE_FILTER ? (int)ck.gen_target : (int)ck.first_start;
+        if (HASGEN) {
+            const uint32_t np = __ldg(a.n_periods + stream_id);
+            if (q0u >= np || q0u >= a.streams[stream_id].tab_cap) {   /* the plan kernel did not reach this chunk: refuse to walk garbage */
+                if (!is_f) atomicExch(a.status, VS_ECUDA);
+                active = false; hi = 0; lo = 0; nstart = 0; orow = nullptr;
             }
         }
     }
+    const VsStream *st = a.streams + stream_id;
     /* windows are anchored on the 16-byte grid of the row's own address in HBM */
     const int phase = (int)((reinterpret_cast<uintptr_t>(orow) >> 1) & 7);
     const int blk0 = nstart - ((phase + nstart) & 7);
@@ -138,17 +140,103 @@ __global__ void __launch_bounds__(VS_NT, MODE == VS_MODE_FLOW ? 3 : 1) vs_render
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nwin = max(nwin, __shfl_xor_sync(VS_FULL, nwin, o));
 
-    /* ---- filter state ------------------------------------------------------------------------------------ */
-    double y[VS_RING], cf[VS_RING];
+    /* =====================================================================================================
+     * F: the order-22 recurrence down the lane's own tile row, in place
+     * =================================================================================================== */
+    if (is_f) {
+        double y[VS_RING], cf[VS_RING];
 #pragma unroll
-    for (int j = 0; j < VS_RING; j++) { y[j] = 0.0; cf[j] = HASFILT ? c_ncoef[preset][j] : 0.0; }
-    int xg_prev = 0;
+        for (int j = 0; j < VS_RING; j++) { y[j] = 0.0; cf[j] = c_ncoef[preset][j]; }
+        const double gaind = active ? (double)st->gain : 0.0, pred = active ? (double)st->pre : 0.0;
+        const int gain_i = (int)gaind, pre_i = (int)pred;
+        double *rrow = (RAW && active && a.raw_out) ? a.raw_out + st->out_off : nullptr;
+        int xg_prev = 0, mbase = blk0, ti = 0;
 
-    /* ---- generator state -------------------------------------------------------------------------------- */
+        vs_pair_barrier(pair);                              /* window 0 generated */
+        for (int w = 0; w < nwin; w++) {
+            unsigned char *trow = smem + tile_off + (uint32_t)ti * TILE + (uint32_t)lane * TSB;
+            ti = ti == NT - 1 ? 0 : ti + 1;
+#pragma unroll 1
+            for (int b = 0; b < WIN / VS_RING; b++) {
+#pragma unroll
+                for (int g = 0; g < VS_RING / VS_GROUP; g++) {
+                    uint4 *piece = reinterpret_cast<uint4 *>(trow + (b * VS_RING + g * VS_GROUP) * 2);
+                    const uint4 xv = *piece;
+                    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+                    uint32_t ow[VS_GROUP / 2];
+                    int qv[VS_GROUP];
+#pragma unroll
+                    for (int u = 0; u < VS_GROUP; u++) {
+                        const int k = g * VS_GROUP + u;
+                        const int xi = (u & 1) ? (int)xw[u >> 1] >> 16 : (int)(int16_t)(xw[u >> 1] & 0xffffu);
+                        double acc, v;
+                        if (FILT == VS_FILT_INT) {
+                            /* gain and pre-emphasis on the integer input; the recurrence then yields the
+                             * pre-emphasised waveform directly (the filter is LTI) */
+                            const int xg = xi * gain_i;
+                            acc = (double)(xg - xg_prev * pre_i);
+                            xg_prev = xg;
+#pragma unroll
+                            for (int j = VS_ORDER; j >= 1; j--) acc = __fma_rn(y[(k + VS_RING - j) % VS_RING], cf[j], acc);
+                            v = acc;
+                        } else if (FILT == VS_FILT_FMA) {
+                            acc = __dmul_rn((double)xi, gaind);                                      /* vowel_new.c:266-269 */
+#pragma unroll
+                            for (int j = VS_ORDER; j >= 1; j--) acc = __fma_rn(y[(k + VS_RING - j) % VS_RING], cf[j], acc);
+                            v = __fma_rn(-pred, y[(k + VS_RING - 1) % VS_RING], acc);                /* :284 */
+                        } else {
+                            acc = __dmul_rn((double)xi, gaind);
+#pragma unroll
+                            for (int j = 1; j <= VS_ORDER; j++)                                      /* :279-281, same order, unfused */
+                                acc = __dsub_rn(acc, __dmul_rn(-cf[j], y[(k + VS_RING - j) % VS_RING]));
+                            v = __dsub_rn(acc, __dmul_rn(pred, y[(k + VS_RING - 1) % VS_RING]));
+                        }
+                        y[k] = acc;                                                                  /* :287-289 (ring) */
+                        /* quantiser: round2int() of vowel_new.c:413-427, literally, in exact mode; otherwise one F2I
+                         * (saturating; ties -- never hit -- go to even), the lower clip here, the upper one in the
+                         * saturating pack below */
+                        qv[u] = FILT == VS_FILT_EXACT ? vs_round2int(v) : max(-32767, __double2int_rn(v));
+                        if (RAW) {
+                            const int m = mbase + u;
+                            if (rrow && m >= lo && m < hi) rrow[m] = v;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < VS_GROUP; u += 2)
+                        asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(ow[u >> 1]) : "r"(qv[u + 1]), "r"(qv[u]));
+                    *piece = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    mbase += VS_GROUP;
+                }
+            }
+            vs_fence_async();                               /* the TMA engine will read what this lane wrote */
+            vs_pair_barrier(pair);                          /* window w filtered; window w+1 generated */
+        }
+        return;
+    }
+
+    /* =====================================================================================================
+     * G: generate (or load) window after window, hand finished windows to the TMA engine
+     * =================================================================================================== */
+    int T2 = 0, DCi = 0, DCs = 0, nper = 0;
+    uint32_t pulse_off = 0xffffffffu;
+    bool nz = false;
+    const unsigned char *ptab = nullptr;                    /* the row's period table */
+    if (HASGEN && active) {
+        ptab = reinterpret_cast<const unsigned char *>(a.table) + st->tab_off * (a.compact ? sizeof(VsPeriodC) : sizeof(VsPeriod));
+        T2 = st->T2;
+        DCi = (int)ceilf(st->DC);                           /* (float)x < DC  <=>  x < ceil(DC) for integer x */
+        DCs = st->DCs;
+        nz = (st->flags & VS_F_NOISE) != 0;
+        pulse_off = st->pulse_off;
+        nper = (int)__ldg(a.n_periods + stream_id);
+    }
+    const int q0 = (int)q0u;
     const int qlast = nper - 1;
     int q = q0 - 1;                                         /* index of the current period                         */
-    /* fast generator: cur = (Adc, Tc, noc), next = (An, Tn, non); ic = in-period index of the group's first sample */
-    int ic = 0, Tc = nstart - blk0, noc = 0, Tn = VS_BIG_T, non = 0;
+    /* fast generator: cur = (Adc, Tc), next = (An, Tn); ic = in-period index of the group's first sample.  Past the
+     * row's last period it keeps running on periods of amplitude 0 and length tpad (never stored) */
+    const int tpad = (HASGEN && active) ? (int)st->tpad : VS_GROUP;
+    int ic = 0, Tc = nstart - blk0, Tn = tpad;
     double Adc = 0.0;
     float An = 0.0f;
     uint32_t tb = cache_off;                                /* the row's pulse table in shared memory (byte offset) */
@@ -159,19 +247,22 @@ __global__ void __launch_bounds__(VS_NT, MODE == VS_MODE_FLOW ? 3 : 1) vs_render
     double sAd = 0.0, sKd = 0.0, sndwd = 0.0;
     const double *gtab = a.costab + (pulse_off == 0xffffffffu ? 0u : pulse_off);
     VsRng rng;
-    rng.r = s_rng + threadIdx.x;
+    rng.r = s_rng + (uint32_t)pair * 32u + (uint32_t)lane;
     rng.f = 3;
 
+    /* A above 32767: x[T2] = (short)ceil(A) < 0, the falling branch is left at once (flowgen_shimmer.c:329) */
     auto nopen_of = [&](float A, int T) -> int { return min(T, A > 32767.0f ? T2 : 2 * T2); };
 
     if (FAST) {
-        /* pulse tables into the warp's cache: one copy per distinct table of the warp's rows (the host sized the
+        /* pulse tables into the pair's cache: one copy per distinct table of the warp's rows (the host sized the
          * cache from the same row order, so everything fits) */
         const uint32_t key = active ? pulse_off : 0xffffffffu;
         const uint32_t grp = __match_any_sync(VS_FULL, key);
         const int leader = __ffs((int)grp) - 1;
+        /* a table is h[0..T2), f[0..T2) and then zeros up to tpad entries: a sample is ceil(A * table[i]) for EVERY
+         * in-period index i, open phase or not (tpad is the same for all rows that share a table) */
         const uint32_t len = active ? 2u * (uint32_t)T2 : 0u;
-        const uint32_t mine = (active && lane == leader) ? len : 0u;
+        const uint32_t mine = (active && lane == leader) ? (uint32_t)tpad : 0u;
         uint32_t incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -186,8 +277,9 @@ __global__ void __launch_bounds__(VS_NT, MODE == VS_MODE_FLOW ? 3 : 1) vs_render
             const int L = __ffs((int)leaders) - 1;
             leaders &= leaders - 1u;
             const uint32_t src = __shfl_sync(VS_FULL, pulse_off, L), n = __shfl_sync(VS_FULL, len, L), dst = __shfl_sync(VS_FULL, base, L);
-            if (dst + n <= a.cache_doubles)
-                for (uint32_t k = lane; k < n; k += 32) cache[dst + k] = __ldg(a.costab + src + k);
+            const uint32_t np = __shfl_sync(VS_FULL, mine, L);
+            if (dst + np <= a.cache_doubles)
+                for (uint32_t k = lane; k < np; k += 32) cache[dst + k] = k < n ? __ldg(a.costab + src + k) : 0.0;
             else if (lane == 0) atomicExch(a.status, VS_ECUDA);
         }
         tb = cache_off + lbase * 8u;
@@ -203,46 +295,49 @@ __global__ void __launch_bounds__(VS_NT, MODE == VS_MODE_FLOW ? 3 : 1) vs_render
         if (active && q0 <= qlast) {
             const uint2 e = *reinterpret_cast<const uint2 *>(smem + ring_off + (((uint32_t)q0 & Rm) * 32u + lane) * 8u);
             An = __uint_as_float(e.x); Tn = (int)e.y;
-            non = nopen_of(An, Tn);
         }
     }
-    if (NOISE && HASGEN && active && nz && nper > 0) {
+    if (NOISE && HASGEN && active && nz) {
         /* the plan kernel's snapshot is taken after the first period's K draw; it is stored with f = 3 */
         for (int k = 0; k < VS_RNG_DEG; k++) rng.r[k * VS_NT] = __ldg(a.rng_snap + (size_t)chunk_id * 32 + k);
     }
+    if (MODE == VS_MODE_FILTER) {
+        VsRowIn *rows = reinterpret_cast<VsRowIn *>(smem + cache_off);
+        VsRowIn r;
+        r.fin = active ? a.flow_in + st->in_off : nullptr;
+        r.nstart = nstart; r.hi = hi;
+        rows[lane] = r;
+        __syncwarp();
+    }
 
-    /* ---- G, fast: 8 samples of the lane's row, branch free -------------------------------------------- */
+    /* ---- G, fast: 8 samples of the lane's row, branch free -------------------------------------------- *
+     * At most one pitch period ends inside a group (T >= 24).  A sample's in-period index is ic+u in the current
+     * period or ic+u-Tc in the next: the unsigned minimum of the two.  Both periods read the same table (T2 and K
+     * belong to the stream); the amplitude is picked by the sign of ic+u-Tc.  With the table zero beyond the open
+     * phase and A <= 32767, flowgen_shimmer.c:319-335 is  x = max(ceil(A * table[i]), (short)DC):  values below DC
+     * become DC (the rising branch's test :320; on the falling branch the first such value ends it, :329, and the
+     * factor only decreases from there), the closed phase is ceil(0) = 0 <= DC. */
     auto gen_fast = [&](int (&x)[VS_GROUP], const bool first) {
-        const int tn = Tc - ic;                             /* samples of the current period left             */
-        const int kb = min(tn, VS_GROUP);                   /* sample u >= kb belongs to the next period      */
-        const int oc = max(min(noc - ic, kb), 0);           /* open-phase samples of the current period       */
-        const int on = min(kb + non, VS_GROUP);             /* the next period is open on [kb, on)            */
-        const uint32_t selm = 0xffu << kb;
-        const uint32_t openm = ((1u << oc) - 1u) | (selm & ((1u << on) - 1u));
-        const uint32_t a_c = tb + (uint32_t)ic * 8u, a_n = tb - (uint32_t)kb * 8u;
+        const int icT = ic - Tc;
         const double Adn = (double)An;
 #pragma unroll
         for (int u = 0; u < VS_GROUP; u++) {
-            const bool ps = ((selm >> u) & 1u) != 0u, po = ((openm >> u) & 1u) != 0u;
-            const uint32_t ad = ps ? a_n : a_c;
-            double fac = 0.0;
-            if (po) fac = *reinterpret_cast<const double *>(smem + ad + u * 8);
-            const double A = ps ? Adn : Adc;
-            /* ceil as a 32-bit integer.  The reference tests the value after its (short) cast: above 32767 it wraps
-             * negative, i.e. below DC (flowgen_shimmer.c:320,329) */
+            const int t2 = icT + u;
+            const uint32_t idx = min((uint32_t)(ic + u), (uint32_t)t2);
+            const bool nx = t2 >= 0;                        /* the sample belongs to the next period */
+            const double fac = *reinterpret_cast<const double *>(smem + tb + idx * 8u);
+            const double A = nx ? Adn : Adc;
             const int v = __double2int_ru(__dmul_rn(A, fac));
-            const bool ok = po && v >= DCi && v <= 32767;
-            x[u] = ok ? v : (first ? (ps ? DCs : 0) : DCs);
+            x[u] = max(v, first ? (nx ? DCs : 0) : DCs);
         }
         /* the group's last sample may have been the period's last: promote `next`, read the entry after it */
-        const bool pr = tn <= VS_GROUP;
+        const bool pr = icT + VS_GROUP >= 0;
         ic += VS_GROUP;
-        if (pr) { ic -= Tc; Adc = Adn; noc = non; Tc = Tn; q++; }
+        if (pr) { ic -= Tc; Adc = Adn; Tc = Tn; q++; }
         const uint2 e = *reinterpret_cast<const uint2 *>(smem + ring_off + ((((uint32_t)(q + 1)) & Rm) * 32u + lane) * 8u);
         const bool valid = q < qlast;
         An = valid ? __uint_as_float(e.x) : 0.0f;
-        Tn = valid ? (int)e.y : VS_BIG_T;
-        non = nopen_of(An, Tn);
+        Tn = valid ? (int)e.y : tpad;
     };
 
     /* keep the ring `ring_ahead` periods ahead of the current one (called once per window) */
@@ -296,105 +391,88 @@ __global__ void __launch_bounds__(VS_NT, MODE == VS_MODE_FLOW ? 3 : 1) vs_render
         return x;
     };
 
-    int mbase = blk0;                                       /* stream index of the next sample to filter / store */
-    auto gen_group = [&](int (&x)[VS_GROUP], const bool first, const int m0) {
+    /* one window of the pair's 32 rows into tile `ti`: generated lane = row, or (filter-only mode) loaded row by
+     * row with the lanes along the row, i.e. coalesced */
+    auto fill_window = [&](const int w, const int ti) {
+        unsigned char *tbase = smem + tile_off + (uint32_t)ti * TILE;
         if (MODE == VS_MODE_FILTER) {
+            const VsRowIn *rows = reinterpret_cast<const VsRowIn *>(smem + cache_off);
+#pragma unroll 4
+            for (int j = 0; j < 32; j++) {
+                const VsRowIn r = rows[j];
+                const int wb = __shfl_sync(VS_FULL, blk0, j) + w * WIN;
+                int16_t *trow = reinterpret_cast<int16_t *>(tbase + j * TSB);
+                if (wb >= r.hi) continue;
 #pragma unroll
-            for (int u = 0; u < VS_GROUP; u++) {
-                const int m = m0 + u;
-                x[u] = (m >= nstart && m < hi) ? (int)__ldg(fin + m) : 0;
+                for (int k = lane; k < WIN; k += 32) {
+                    const int m = wb + k;
+                    trow[k] = (m >= r.nstart && m < r.hi) ? __ldg(r.fin + m) : (int16_t)0;
+                }
             }
-        } else if (FAST) {
-            gen_fast(x, first);
-        } else {
+            __syncwarp();
+            return;
+        }
+        unsigned char *trow = tbase + (uint32_t)lane * TSB;
+        if (FAST) ring_refill();
 #pragma unroll 1
-            for (int u = 0; u < VS_GROUP; u++) x[u] = gen_simple();
+        for (int g = 0; g < NGRP; g++) {
+            int x[VS_GROUP];
+            if (FAST) {
+                if (w == 0 && g == 0) gen_fast(x, true);
+                else gen_fast(x, false);
+            } else {
+#pragma unroll
+                for (int u = 0; u < VS_GROUP; u++) x[u] = gen_simple();
+            }
+            uint32_t ow[VS_GROUP / 2];
+#pragma unroll
+            for (int u = 0; u < VS_GROUP; u += 2) ow[u >> 1] = ((uint32_t)x[u] & 0xffffu) | ((uint32_t)x[u + 1] << 16);
+            *reinterpret_cast<uint4 *>(trow + g * VS_GROUP * 2) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
     };
 
-    /* ---- F: 8 samples of the recurrence at ring positions k0.., packed into one 16-byte piece ---------- */
-    auto quant = [&](double v) -> int {
-        if (FILT == VS_FILT_EXACT) return vs_round2int(v);                       /* vowel_new.c:413-427, literally */
-        return max(-32767, min(32767, __double2int_rn(v)));                     /* F2I saturates; ties (never hit) go to even */
-    };
-
-    /* ---- W: the finished window leaves through the TMA engine ------------------------------------------ */
-    auto store_window = [&](const int w) {
+    /* ---- W: a finished window leaves through the TMA engine: per lane one bulk copy of its row's whole 16-byte
+     * pieces inside [lo, hi); the few samples of a stream's unaligned first / last piece go as 2-byte stores ---- */
+    auto store_window = [&](const int w, const int ti) {
         const int wb = blk0 + w * WIN;
         const int a0 = max(wb, lo), b0 = min(wb + WIN, hi);
-        vs_fence_async();
         if (b0 > a0) {
-            const uint32_t trow = tile_off + (uint32_t)(w & 1) * TILE + (uint32_t)lane * TSB;
+            const uint32_t trow = tile_off + (uint32_t)ti * TILE + (uint32_t)lane * TSB;
             const int a8 = wb + ((a0 - wb + 7) & ~7), b8 = wb + ((b0 - wb) & ~7);
             if (b8 > a8) vs_bulk_s2g(orow + a8, smem_base + trow + (uint32_t)(a8 - wb) * 2u, (uint32_t)(b8 - a8) * 2u);
             const int16_t *tr = reinterpret_cast<const int16_t *>(smem + trow);
             const int hend = min(a8, b0);
-            for (int m = a0; m < hend; m++) orow[m] = tr[m - wb];               /* a stream's first and last few samples */
+            for (int m = a0; m < hend; m++) orow[m] = tr[m - wb];
             for (int m = max(b8, hend); m < b0; m++) orow[m] = tr[m - wb];
         }
         vs_bulk_commit();
     };
 
-    /* ======== the row, window by window ======== */
-    int xn[VS_GROUP];
-    gen_group(xn, true, blk0);
-    for (int w = 0; w < nwin; w++) {
-        if (FAST) ring_refill();
-        if (w >= 2) vs_bulk_wait_read<1>();                 /* the copy that last read this tile has finished */
-        unsigned char *trow = smem + tile_off + (uint32_t)(w & 1) * TILE + (uint32_t)lane * TSB;
-#pragma unroll 1
-        for (int b = 0; b < WIN / VS_RING; b++) {
-#pragma unroll
-            for (int g = 0; g < VS_RING / VS_GROUP; g++) {
-                int xc[VS_GROUP];
-#pragma unroll
-                for (int u = 0; u < VS_GROUP; u++) xc[u] = xn[u];
-                gen_group(xn, false, mbase + VS_GROUP);     /* one group ahead: its latency hides behind the filter */
-                uint32_t ow[VS_GROUP / 2];
-#pragma unroll
-                for (int u = 0; u < VS_GROUP; u++) {
-                    const int k = g * VS_GROUP + u;
-                    int qv;
-                    if (!HASFILT) {
-                        qv = xc[u];
-                    } else {
-                        double acc, v;
-                        if (FILT == VS_FILT_INT) {
-                            /* gain and pre-emphasis on the integer input; the recurrence then yields the
-                             * pre-emphasised waveform directly (the filter is LTI) */
-                            const int xg = xc[u] * gain_i;
-                            acc = (double)(xg - xg_prev * pre_i);
-                            xg_prev = xg;
-#pragma unroll
-                            for (int j = VS_ORDER; j >= 1; j--) acc = __fma_rn(y[(k + VS_RING - j) % VS_RING], cf[j], acc);
-                            v = acc;
-                        } else if (FILT == VS_FILT_FMA) {
-                            acc = __dmul_rn((double)xc[u], gaind);                                   /* vowel_new.c:266-269 */
-#pragma unroll
-                            for (int j = VS_ORDER; j >= 1; j--) acc = __fma_rn(y[(k + VS_RING - j) % VS_RING], cf[j], acc);
-                            v = __fma_rn(-pred, y[(k + VS_RING - 1) % VS_RING], acc);                /* :284 */
-                        } else {
-                            acc = __dmul_rn((double)xc[u], gaind);
-#pragma unroll
-                            for (int j = 1; j <= VS_ORDER; j++)                                      /* :279-281, same order, unfused */
-                                acc = __dsub_rn(acc, __dmul_rn(-cf[j], y[(k + VS_RING - j) % VS_RING]));
-                            v = __dsub_rn(acc, __dmul_rn(pred, y[(k + VS_RING - 1) % VS_RING]));
-                        }
-                        y[k] = acc;                                                                  /* :287-289 (ring) */
-                        qv = quant(v);
-                        if (RAW) {
-                            const int m = mbase + u;
-                            if (rrow && m >= lo && m < hi) rrow[m] = v;
-                        }
-                    }
-                    if (u & 1) ow[u >> 1] |= (uint32_t)qv << 16;
-                    else ow[u >> 1] = (uint32_t)qv & 0xffffu;
-                }
-                *reinterpret_cast<uint4 *>(trow + (b * VS_RING + g * VS_GROUP) * 2) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                mbase += VS_GROUP;
-            }
+    if (!HASFILT) {
+        /* ======== flow only: generate, store, next tile ======== */
+        int ti = 0;
+        for (int w = 0; w < nwin; w++) {
+            vs_bulk_wait_read<NT - 1>();                    /* the copy that last read this tile has finished */
+            fill_window(w, ti);
+            vs_fence_async();
+            store_window(w, ti);
+            ti = ti == NT - 1 ? 0 : ti + 1;
         }
-        store_window(w);
+    } else {
+        /* ======== G runs one window ahead of F; three tiles: F's, G's, and the one the TMA engine reads ======== */
+        int ti = 0;                                         /* tile of window w */
+        if (nwin > 0) fill_window(0, 0);
+        vs_pair_barrier(pair);                              /* window 0 generated */
+        for (int w = 0; w < nwin; w++) {
+            const int tn1 = ti == NT - 1 ? 0 : ti + 1;
+            if (w + 1 < nwin) {
+                vs_bulk_wait_read<1>();                     /* the copy of window w-2 has finished reading tile tn1 */
+                fill_window(w + 1, tn1);
+            }
+            vs_pair_barrier(pair);                          /* window w filtered (and fenced) by F */
+            store_window(w, ti);
+            ti = tn1;
+        }
     }
     vs_bulk_wait_read<0>();                                 /* shared memory must outlive the copies that read it */
 }
@@ -411,12 +489,13 @@ cudaError_t vs_render_init_device()
 }
 
 int vs_render_window(int mode) { return vs_win(mode); }
+int vs_render_tiles(int mode) { return VS_RENDER_TILES(mode); }
 
 template <int MODE, int GEN, bool NOISE, int FILT, bool RAW>
 static cudaError_t vs_go(const VsRenderArgs &a, cudaStream_t s)
 {
     const unsigned grid = a.n_rows / VS_NT;
-    const int dyn = 4 * (int)a.warp_bytes + (NOISE ? VS_RNG_DEG * VS_NT * 4 : 0);
+    const int dyn = 4 * (int)a.warp_bytes + (NOISE ? VS_RNG_DEG * VS_NT * 4 : 0);      /* warp_bytes: per pair of warps */
     /* the attribute is per device and per kernel: set it whenever a launch needs more than the last one did */
     static int granted[16] = {0};
     int dev = 0;
@@ -428,7 +507,7 @@ static cudaError_t vs_go(const VsRenderArgs &a, cudaStream_t s)
     } else if (dev >= 16) {
         cudaFuncSetAttribute(vs_render_kernel<MODE, GEN, NOISE, FILT, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     }
-    vs_render_kernel<MODE, GEN, NOISE, FILT, RAW><<<grid, VS_NT, dyn, s>>>(a);
+    vs_render_kernel<MODE, GEN, NOISE, FILT, RAW><<<grid, VS_RENDER_THREADS(MODE), dyn, s>>>(a);
     return cudaGetLastError();
 }
 
