@@ -70,6 +70,79 @@ __device__ __forceinline__ void vs_pair_barrier(int pair)
     asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
 }
 
+/* ---- F: one lane, one row: the order-22 recurrence (vowel_new.c:266-289) window after window, in place ------- */
+template <int WIN, int NT, int FILT, bool RAW, int PRESET>
+__device__ __forceinline__ void vs_filter_rows(unsigned char *tiles /* the lane's row in tile 0 */, const int pair, const int nwin,
+                                               const double gaind, const double pred, double *rrow, const int blk0, const int lo, const int hi)
+{
+    constexpr int TILE = 32 * WIN * 2;
+    double y[VS_RING];
+#pragma unroll
+    for (int j = 0; j < VS_RING; j++) y[j] = 0.0;
+    const int gain_i = (int)gaind, pre_i = (int)pred;
+    int xg_prev = 0, mbase = blk0, ti = 0;
+
+    vs_pair_barrier(pair);                                  /* window 0 generated */
+    for (int w = 0; w < nwin; w++) {
+        unsigned char *trow = tiles + (uint32_t)ti * TILE;
+        ti = ti == NT - 1 ? 0 : ti + 1;
+#pragma unroll 1
+        for (int b = 0; b < WIN / VS_RING; b++) {
+#pragma unroll
+            for (int g = 0; g < VS_RING / VS_GROUP; g++) {
+                uint4 *piece = reinterpret_cast<uint4 *>(trow + (b * VS_RING + g * VS_GROUP) * 2);
+                const uint4 xv = *piece;
+                const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+                uint32_t ow[VS_GROUP / 2];
+                int qv[VS_GROUP];
+#pragma unroll
+                for (int u = 0; u < VS_GROUP; u++) {
+                    const int k = g * VS_GROUP + u;
+                    const int xi = (u & 1) ? (int)xw[u >> 1] >> 16 : (int)(int16_t)(xw[u >> 1] & 0xffffu);
+                    double acc, v;
+                    if (FILT == VS_FILT_INT) {
+                        /* gain and pre-emphasis on the integer input; the recurrence then yields the
+                         * pre-emphasised waveform directly (the filter is LTI) */
+                        const int xg = xi * gain_i;
+                        acc = (double)(xg - xg_prev * pre_i);
+                        xg_prev = xg;
+#pragma unroll
+                        for (int j = VS_ORDER; j >= 1; j--) acc = __fma_rn(y[(k + VS_RING - j) % VS_RING], c_ncoef[PRESET][j], acc);
+                        v = acc;
+                    } else if (FILT == VS_FILT_FMA) {
+                        acc = __dmul_rn((double)xi, gaind);                                          /* vowel_new.c:266-269 */
+#pragma unroll
+                        for (int j = VS_ORDER; j >= 1; j--) acc = __fma_rn(y[(k + VS_RING - j) % VS_RING], c_ncoef[PRESET][j], acc);
+                        v = __fma_rn(-pred, y[(k + VS_RING - 1) % VS_RING], acc);                    /* :284 */
+                    } else {
+                        acc = __dmul_rn((double)xi, gaind);
+#pragma unroll
+                        for (int j = 1; j <= VS_ORDER; j++)                                          /* :279-281, same order, unfused */
+                            acc = __dsub_rn(acc, __dmul_rn(-c_ncoef[PRESET][j], y[(k + VS_RING - j) % VS_RING]));
+                        v = __dsub_rn(acc, __dmul_rn(pred, y[(k + VS_RING - 1) % VS_RING]));
+                    }
+                    y[k] = acc;                                                                      /* :287-289 (ring) */
+                    /* quantiser: round2int() of vowel_new.c:413-427, literally, in exact mode; otherwise one F2I
+                     * (saturating; ties -- never hit -- go to even), the lower clip here, the upper one in the
+                     * saturating pack below */
+                    qv[u] = FILT == VS_FILT_EXACT ? vs_round2int(v) : max(-32767, __double2int_rn(v));
+                    if (RAW) {
+                        const int m = mbase + u;
+                        if (rrow && m >= lo && m < hi) rrow[m] = v;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < VS_GROUP; u += 2)
+                    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(ow[u >> 1]) : "r"(qv[u + 1]), "r"(qv[u]));
+                *piece = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                mbase += VS_GROUP;
+            }
+        }
+        vs_fence_async();                                   /* the TMA engine will read what this lane wrote */
+        vs_pair_barrier(pair);                              /* window w filtered; window w+1 generated */
+    }
+}
+
 /* what the loader warp of the filter-only mode needs to know about a row */
 struct __align__(16) VsRowIn {
     const int16_t *fin;
@@ -96,7 +169,7 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
     const int pair = warp & 3;
     const bool is_f = HASFILT && warp < 4;
 
-    /* vowel preset of this CTA: uniform by construction */
+    /* vowel preset of this CTA: a function of blockIdx and kernel parameters */
     int preset = 0;
     if (HASFILT) {
 #pragma unroll
@@ -141,75 +214,20 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
     for (int o = 16; o > 0; o >>= 1) nwin = max(nwin, __shfl_xor_sync(VS_FULL, nwin, o));
 
     /* =====================================================================================================
-     * F: the order-22 recurrence down the lane's own tile row, in place
+     * F: the order-22 recurrence down the lane's own tile row, in place.  One copy of the loop per vowel preset:
+     * the coefficients are then constant-bank operands of the DFMAs at literal addresses (a DFMA with two
+     * register operands and one constant operand issues every ~2.2 cycles per sub-partition, the three-register
+     * form only every ~3.1: tests/tools/dfma_ops.cu).  A CTA runs one preset, so one copy is hot per SM.
      * =================================================================================================== */
     if (is_f) {
-        double y[VS_RING], cf[VS_RING];
-#pragma unroll
-        for (int j = 0; j < VS_RING; j++) { y[j] = 0.0; cf[j] = c_ncoef[preset][j]; }
         const double gaind = active ? (double)st->gain : 0.0, pred = active ? (double)st->pre : 0.0;
-        const int gain_i = (int)gaind, pre_i = (int)pred;
         double *rrow = (RAW && active && a.raw_out) ? a.raw_out + st->out_off : nullptr;
-        int xg_prev = 0, mbase = blk0, ti = 0;
-
-        vs_pair_barrier(pair);                              /* window 0 generated */
-        for (int w = 0; w < nwin; w++) {
-            unsigned char *trow = smem + tile_off + (uint32_t)ti * TILE + (uint32_t)lane * TSB;
-            ti = ti == NT - 1 ? 0 : ti + 1;
-#pragma unroll 1
-            for (int b = 0; b < WIN / VS_RING; b++) {
-#pragma unroll
-                for (int g = 0; g < VS_RING / VS_GROUP; g++) {
-                    uint4 *piece = reinterpret_cast<uint4 *>(trow + (b * VS_RING + g * VS_GROUP) * 2);
-                    const uint4 xv = *piece;
-                    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-                    uint32_t ow[VS_GROUP / 2];
-                    int qv[VS_GROUP];
-#pragma unroll
-                    for (int u = 0; u < VS_GROUP; u++) {
-                        const int k = g * VS_GROUP + u;
-                        const int xi = (u & 1) ? (int)xw[u >> 1] >> 16 : (int)(int16_t)(xw[u >> 1] & 0xffffu);
-                        double acc, v;
-                        if (FILT == VS_FILT_INT) {
-                            /* gain and pre-emphasis on the integer input; the recurrence then yields the
-                             * pre-emphasised waveform directly (the filter is LTI) */
-                            const int xg = xi * gain_i;
-                            acc = (double)(xg - xg_prev * pre_i);
-                            xg_prev = xg;
-#pragma unroll
-                            for (int j = VS_ORDER; j >= 1; j--) acc = __fma_rn(y[(k + VS_RING - j) % VS_RING], cf[j], acc);
-                            v = acc;
-                        } else if (FILT == VS_FILT_FMA) {
-                            acc = __dmul_rn((double)xi, gaind);                                      /* vowel_new.c:266-269 */
-#pragma unroll
-                            for (int j = VS_ORDER; j >= 1; j--) acc = __fma_rn(y[(k + VS_RING - j) % VS_RING], cf[j], acc);
-                            v = __fma_rn(-pred, y[(k + VS_RING - 1) % VS_RING], acc);                /* :284 */
-                        } else {
-                            acc = __dmul_rn((double)xi, gaind);
-#pragma unroll
-                            for (int j = 1; j <= VS_ORDER; j++)                                      /* :279-281, same order, unfused */
-                                acc = __dsub_rn(acc, __dmul_rn(-cf[j], y[(k + VS_RING - j) % VS_RING]));
-                            v = __dsub_rn(acc, __dmul_rn(pred, y[(k + VS_RING - 1) % VS_RING]));
-                        }
-                        y[k] = acc;                                                                  /* :287-289 (ring) */
-                        /* quantiser: round2int() of vowel_new.c:413-427, literally, in exact mode; otherwise one F2I
-                         * (saturating; ties -- never hit -- go to even), the lower clip here, the upper one in the
-                         * saturating pack below */
-                        qv[u] = FILT == VS_FILT_EXACT ? vs_round2int(v) : max(-32767, __double2int_rn(v));
-                        if (RAW) {
-                            const int m = mbase + u;
-                            if (rrow && m >= lo && m < hi) rrow[m] = v;
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < VS_GROUP; u += 2)
-                        asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(ow[u >> 1]) : "r"(qv[u + 1]), "r"(qv[u]));
-                    *piece = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                    mbase += VS_GROUP;
-                }
-            }
-            vs_fence_async();                               /* the TMA engine will read what this lane wrote */
-            vs_pair_barrier(pair);                          /* window w filtered; window w+1 generated */
+        unsigned char *tiles = smem + tile_off + (uint32_t)lane * TSB;
+        switch (preset) {
+#define VS_F_CASE(P) case P: vs_filter_rows<WIN, NT, FILT, RAW, P>(tiles, pair, nwin, gaind, pred, rrow, blk0, lo, hi); break;
+            VS_F_CASE(0) VS_F_CASE(1) VS_F_CASE(2) VS_F_CASE(3) VS_F_CASE(4) VS_F_CASE(5) VS_F_CASE(6) VS_F_CASE(7) VS_F_CASE(8)
+            default: vs_filter_rows<WIN, NT, FILT, RAW, 9>(tiles, pair, nwin, gaind, pred, rrow, blk0, lo, hi); break;
+#undef VS_F_CASE
         }
         return;
     }
