@@ -98,6 +98,7 @@ struct vs_ctx {
     int opt_slab = 0;
     double opt_warps = 2.0;
     int opt_async_host = 0;
+    int opt_debug = 0;
     int opt_simple_gen = 0;      /* 1: never use the branch-free generator (debug / A-B) */
     std::vector<double> cos_host;
     std::map<int, uint32_t> cos_index;
@@ -427,10 +428,13 @@ uint32_t choose_chunk(vs_ctx *ctx, const Slot &slot, int mode, size_t n_streams,
     const double smsp = (double)slot.sm_count * 4.0;
     const double avg_n = (double)total / (double)n_streams;
     if (mode == VS_MODE_FLOW) {
-        const double want_threads = smsp * 32.0 * 8.0 * ctx->opt_warps;
-        if ((double)n_streams >= want_threads) return 0;
-        double L = std::ceil((double)total / want_threads);
-        if (L < 1024.0) L = 1024.0;
+        /* the flow has no carry, chunks are free: one full wave of rows (4 CTAs of VS_NT rows per SM), or whole
+         * waves of >= 512-sample chunks when the batch is small */
+        (void)smsp; (void)avg_n;
+        const double lanes = (double)slot.sm_count * 4.0 * VS_NT * 0.97;
+        if ((double)n_streams >= lanes) return 0;
+        double L = std::ceil((double)total / lanes);
+        if (L < 512.0) L = 512.0;
         return ((uint32_t)L + 7u) & ~7u;
     }
     double best_cost = 1e300;
@@ -747,7 +751,9 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             std::sort(ids.begin(), ids.end(), [&](uint32_t x, uint32_t y) {
                 const int px = preset_of(x), py = preset_of(y);
                 if (px != py) return px < py;
-                const uint32_t wx = (hc[x].emit_hi - hc[x].gen_target) >> 6, wy = (hc[y].emit_hi - hc[y].gen_target) >> 6;
+                /* (flow-only chunks are all about one length: keep rows that share a pulse table together instead) */
+                const uint32_t wx = b.mode == VS_MODE_FLOW ? 0u : (hc[x].emit_hi - hc[x].gen_target) >> 6;
+                const uint32_t wy = b.mode == VS_MODE_FLOW ? 0u : (hc[y].emit_hi - hc[y].gen_target) >> 6;
                 if (wx != wy) return wx > wy;
                 const uint32_t tx = hs[s0 + hc[x].stream].pulse_off, ty = hs[s0 + hc[y].stream].pulse_off;
                 if (tx != ty) return tx < ty;
@@ -992,6 +998,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             ra.pcm_out = d_pcm;
             ra.raw_out = d_raw;
             ra.general_pulse = any_kvar ? 1 : 0;
+            ra.debug = (uint32_t)ctx->opt_debug;
             ra.status = (int32_t *)sl.status[cp].p;
             /* shared-memory geometry.  The fast generator keeps, per lane, a ring of upcoming period entries (filled
              * one window ahead) and, per warp, the pulse tables of its rows; when the pitch periods of the batch are
@@ -999,7 +1006,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             const int win = vs_render_window(b.mode);
             const uint32_t tile_bytes = (uint32_t)vs_render_tiles(b.mode) * 32u * (uint32_t)win * 2u;
             int gen = VS_GEN_SIMPLE;
-            ra.warp_bytes = tile_bytes + (b.mode == VS_MODE_FILTER ? 32u * 16u : 0u);      /* filter-only: row descriptors of the loader */
+            ra.warp_bytes = tile_bytes;
             if (b.mode != VS_MODE_FILTER && compact && amp_fits && !ctx->opt_simple_gen && t_min >= 24 && t_max <= 8192) {
                 const uint32_t per_win = (uint32_t)(win / t_min) + 2u;      /* pitch periods a lane can start in one window */
                 const uint32_t ahead = 2u * per_win + 3u;
@@ -1007,7 +1014,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 while (R < ahead) R <<= 1;
                 const uint32_t cache = (sl.plan_geom[k].cache_doubles + 1u) & ~1u;
                 const uint32_t wbytes = tile_bytes + R * 256u + cache * 8u;
-                if (R <= 64 && 4u * wbytes <= (b.mode == VS_MODE_FLOW ? 72u : 200u) * 1024u) {
+                if (R <= 64 && 4u * wbytes <= (b.mode == VS_MODE_FLOW ? 100u : 200u) * 1024u) {
                     gen = VS_GEN_FAST;
                     ra.warp_bytes = wbytes; ra.ring_R = R; ra.ring_fetch = per_win + 2u; ra.ring_ahead = ahead; ra.cache_doubles = cache;
                 }
@@ -1199,6 +1206,7 @@ int vs_ctx_set_option(vs_ctx *ctx, int option, double value)
     case VS_OPT_ASYNC_HOST: ctx->opt_async_host = value != 0.0; return VS_OK;
     case VS_OPT_PLAN_WARPS: ctx->opt_plan_warps = value < 0 ? -1 : (value != 0.0); return VS_OK;
     case VS_OPT_SIMPLE_GEN: ctx->opt_simple_gen = value != 0.0; return VS_OK;
+    case 100: ctx->opt_debug = (int)value; return VS_OK;             /* undocumented: timing experiments */
     default: return VS_EINVAL;
     }
 }

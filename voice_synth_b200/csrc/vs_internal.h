@@ -123,6 +123,7 @@ struct VsRenderArgs {
     uint32_t        ring_fetch;     /* entries a lane may fetch per window                           */
     uint32_t        ring_ahead;     /* how far beyond the current period the ring is kept filled     */
     uint32_t        cache_doubles;  /* pulse-table cache per warp                                    */
+    uint32_t        debug;          /* timing experiments (VS_OPT_DEBUG): bit 0 = skip the bulk stores */
 };
 
 /* vowel -n (N1): one entry per stream */

@@ -146,17 +146,13 @@ __device__ __forceinline__ void vs_filter_rows(unsigned char *tiles /* the lane'
     }
 }
 
-/* what the loader warp of the filter-only mode needs to know about a row */
-struct __align__(16) VsRowIn {
-    const int16_t *fin;
-    int32_t nstart, hi;
-};
-
 #define VS_RENDER_THREADS(MODE) ((MODE) == VS_MODE_FLOW ? VS_NT : 2 * VS_NT)
-#define VS_RENDER_TILES(MODE)   ((MODE) == VS_MODE_FLOW ? 2 : 3)
+/* tiles per 32 rows.  Fused / filter-only: F's, G's and the one the TMA engine reads.  Flow only: one -- four CTAs
+ * share an SM and the other warps run while a warp waits for its tile to be read out */
+#define VS_RENDER_TILES(MODE)   ((MODE) == VS_MODE_FLOW ? 1 : 3)
 
 template <int MODE, int GEN, bool NOISE, int FILT, bool RAW>
-__global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW ? 3 : 1) vs_render_kernel(const VsRenderArgs a)
+__global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW ? 4 : 1) vs_render_kernel(const VsRenderArgs a)
 {
     constexpr int WIN = vs_win(MODE), TSB = WIN * 2, TILE = 32 * TSB, NGRP = WIN / VS_GROUP;
     constexpr int NT = VS_RENDER_TILES(MODE);
@@ -322,14 +318,7 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
         /* the plan kernel's snapshot is taken after the first period's K draw; it is stored with f = 3 */
         for (int k = 0; k < VS_RNG_DEG; k++) rng.r[k * VS_NT] = __ldg(a.rng_snap + (size_t)chunk_id * 32 + k);
     }
-    if (MODE == VS_MODE_FILTER) {
-        VsRowIn *rows = reinterpret_cast<VsRowIn *>(smem + cache_off);
-        VsRowIn r;
-        r.fin = active ? a.flow_in + st->in_off : nullptr;
-        r.nstart = nstart; r.hi = hi;
-        rows[lane] = r;
-        __syncwarp();
-    }
+    const int16_t *fin = (MODE == VS_MODE_FILTER && active) ? a.flow_in + st->in_off : nullptr;
 
     /* ---- G, fast: 8 samples of the lane's row, branch free -------------------------------------------- *
      * At most one pitch period ends inside a group (T >= 24).  A sample's in-period index is ic+u in the current
@@ -416,20 +405,30 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
     auto fill_window = [&](const int w, const int ti) {
         unsigned char *tbase = smem + tile_off + (uint32_t)ti * TILE;
         if (MODE == VS_MODE_FILTER) {
-            const VsRowIn *rows = reinterpret_cast<const VsRowIn *>(smem + cache_off);
-#pragma unroll 4
-            for (int j = 0; j < 32; j++) {
-                const VsRowIn r = rows[j];
-                const int wb = __shfl_sync(VS_FULL, blk0, j) + w * WIN;
-                int16_t *trow = reinterpret_cast<int16_t *>(tbase + j * TSB);
-                if (wb >= r.hi) continue;
+            /* lane = row.  Where the input row has the 16-byte phase of the output row (dense layouts) the lane
+             * fetches its window as whole 16-byte pieces, all requested before the first is used: one memory
+             * latency per window.  Any other layout, and the pieces that straddle the row's ends, go sample by
+             * sample. */
+            unsigned char *trow = tbase + (uint32_t)lane * TSB;
+            const int wb = blk0 + w * WIN;
+            const bool aligned = ((reinterpret_cast<uintptr_t>(fin + blk0)) & 15) == 0;
+            uint4 pc[NGRP];
 #pragma unroll
-                for (int k = lane; k < WIN; k += 32) {
-                    const int m = wb + k;
-                    trow[k] = (m >= r.nstart && m < r.hi) ? __ldg(r.fin + m) : (int16_t)0;
+            for (int g = 0; g < NGRP; g++) {
+                const int m0 = wb + g * VS_GROUP;
+                if (aligned && m0 >= nstart && m0 + VS_GROUP <= hi) pc[g] = __ldg(reinterpret_cast<const uint4 *>(fin + m0));
+                else {
+                    uint32_t h[VS_GROUP];
+#pragma unroll
+                    for (int u = 0; u < VS_GROUP; u++) {
+                        const int m = m0 + u;
+                        h[u] = (m >= nstart && m < hi) ? (uint32_t)(uint16_t)__ldg(fin + m) : 0u;
+                    }
+                    pc[g] = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
                 }
             }
-            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < NGRP; g++) *reinterpret_cast<uint4 *>(trow + g * VS_GROUP * 2) = pc[g];
             return;
         }
         unsigned char *trow = tbase + (uint32_t)lane * TSB;
@@ -459,7 +458,7 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
         if (b0 > a0) {
             const uint32_t trow = tile_off + (uint32_t)ti * TILE + (uint32_t)lane * TSB;
             const int a8 = wb + ((a0 - wb + 7) & ~7), b8 = wb + ((b0 - wb) & ~7);
-            if (b8 > a8) vs_bulk_s2g(orow + a8, smem_base + trow + (uint32_t)(a8 - wb) * 2u, (uint32_t)(b8 - a8) * 2u);
+            if (b8 > a8 && !(a.debug & 1)) vs_bulk_s2g(orow + a8, smem_base + trow + (uint32_t)(a8 - wb) * 2u, (uint32_t)(b8 - a8) * 2u);
             const int16_t *tr = reinterpret_cast<const int16_t *>(smem + trow);
             const int hend = min(a8, b0);
             for (int m = a0; m < hend; m++) orow[m] = tr[m - wb];
