@@ -1,10 +1,11 @@
 /* noisecheck.c -- the glottal-noise sample of flowgen_shimmer.c:387,394 in two FP64 operations.
  *
  * reference:  w = (short)ceil((1.0*random()/RAND_MAX)*NDW - NDW/2.0)           (divide, multiply, subtract, ceil)
- * kernel:     t = fma((double)r, fl(1/M), -0.5)   [t = 0.5 exactly when r == M];   w = ceil(t * (double)NDW)
+ * kernel:     t = fma((double)min(r, M-1), fl(1/M), -0.5);   w = ceil(t * (double)NDW)
  *
  * Why they agree: the exact value is NDW*(2r-M)/(2M), M = 2^31-1 prime.  It is an integer only for r = 0 or r = M
- * (M divides neither NDW < M nor 2r-M otherwise), where both forms are exact.  Everywhere else it is at least
+ * (M divides neither NDW < M nor 2r-M otherwise): r = 0 is exact in both forms; at r = M the kernel evaluates r = M-1
+ * instead, NDW/2 - NDW/(2M), which has the ceiling of NDW/2 because NDW/(2M) < 1/2.  Everywhere else it is at least
  * 1/(2M) ~ 2^-32 away from the nearest integer, while both floating-point forms err by less than 2^-34 for
  * NDW < 2^19 -- so neither can cross an integer and both ceilings equal the exact ceiling.
  *
@@ -29,7 +30,7 @@ static int w_ref(int32_t r, int32_t ndw)
 }
 static int w_fast(int32_t r, int32_t ndw)
 {
-    double t = r == 2147483647 ? 0.5 : fma((double)r, INV_M, -0.5);
+    double t = fma((double)(r < 2147483646 ? r : 2147483646), INV_M, -0.5);
     volatile double p = t * (double)ndw;
     return (int)(short)(int32_t)ceil(p);
 }

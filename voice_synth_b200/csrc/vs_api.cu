@@ -533,6 +533,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
     bool int_filter = true;          /* every stream: integral gain, pre-emphasis 0 or 1 -> both commute to the integer input */
     int t_min = 0x7fffffff, t_max = 0;   /* bounds on the pitch period lengths of the batch */
     bool amp_fits = true;            /* no amplitude can pass 32767 (fast generator) */
+    bool noise_simple = true;        /* every noisy stream has DC <= 1 (then T4 == 0) and T2 >= 16: 16-byte period entries do */
     for (size_t i = 0; i < n; i++) {
         VsStream &s = hs[i];
         memset(&s, 0, sizeof s);
@@ -555,6 +556,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             s.DCs = (int16_t)(int32_t)r.DC;                            /* x[i] = par.DC (:321,:335) */
             s.tab_cap = row_max_periods(r, s.n, s.P);
             any_noise |= (r.flags & VS_F_NOISE) != 0;
+            if ((r.flags & VS_F_NOISE) && !(r.DC <= 1.0f && s.T2 >= 16)) noise_simple = false;
             {   /* accepted periods satisfy 0.8*P <= T <= 1.2*P (flowgen_shimmer.c:290) */
                 const bool jit = (r.flags & VS_F_JITTER) && r.jitter != 0.0f;
                 t_min = std::min(t_min, jit ? std::max(1, (int)std::floor(0.8f * (float)P)) : P);
@@ -628,7 +630,8 @@ int run_batch(vs_ctx *ctx, const Batch &b)
     memset(&ctx->timing, 0, sizeof ctx->timing);
     ctx->timing_pending = true;
     const bool exact = ctx->opt_exact != 0;
-    const bool compact = !(any_noise || any_kvar);           /* 8-byte period table entries (amplitude, length) suffice */
+    /* period table format: 8-byte entries (amplitude, length) where they suffice, 16-byte ones for plain glottal noise */
+    const int compact = (any_kvar || want_log) ? VS_TAB_FULL : !any_noise ? VS_TAB_C8 : noise_simple ? VS_TAB_N16 : VS_TAB_FULL;
 
     /* ---- 4. per slot: descriptors up, then slabs of plan -> render -> copy ------------------- */
     for (size_t g = 0; g < nslots; g++) {
@@ -827,7 +830,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         if ((rc = dev_reserve(ctx, sl, sl.nper[cp], ns * sizeof(uint32_t)))) return rc;
         if ((rc = dev_reserve(ctx, sl, sl.status[cp], sizeof(int32_t)))) return rc;
         if (b.mode != VS_MODE_FILTER) {
-            if ((rc = dev_reserve(ctx, sl, sl.table[cp], (tab_total + 8) * (compact ? sizeof(VsPeriodC) : sizeof(VsPeriod))))) return rc;
+            if ((rc = dev_reserve(ctx, sl, sl.table[cp], (tab_total + 8) * VS_TAB_ENTRY_BYTES(compact)))) return rc;
             if (any_noise && (rc = dev_reserve(ctx, sl, sl.snap[cp], nc * 32 * sizeof(uint32_t)))) return rc;
             if ((rc = dev_reserve(ctx, sl, sl.costab, (ctx->cos_host.size() + VS_COS_SLACK) * sizeof(double)))) return rc;
             if (sl.costab_uploaded != ctx->cos_host.size()) {
@@ -931,7 +934,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 pa.n_streams = (uint32_t)(a1 - a0);
                 pa.chunks = (VsChunk *)sl.chunks[cp].p;
                 pa.table = sl.table[cp].p;
-                pa.compact = compact ? 1 : 0;
+                pa.compact = compact;
                 pa.rng_snap = any_noise ? (uint32_t *)sl.snap[cp].p : nullptr;
                 pa.n_periods = (uint32_t *)sl.nper[cp].p + (a0 - s0);
                 pa.costab = (const double *)sl.costab.p;
@@ -990,7 +993,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             ra.n_rows = (uint32_t)(slab_r0[k + 1] - slab_r0[k]);
             memcpy(ra.cta_end, sl.plan_geom[k].cta_end, sizeof ra.cta_end);
             ra.table = sl.table[cp].p;
-            ra.compact = compact ? 1 : 0;
+            ra.compact = compact;
             ra.n_periods = (const uint32_t *)sl.nper[cp].p;
             ra.rng_snap = any_noise ? (const uint32_t *)sl.snap[cp].p : nullptr;
             ra.costab = (const double *)sl.costab.p;
@@ -1007,13 +1010,13 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             const uint32_t tile_bytes = (uint32_t)vs_render_tiles(b.mode) * 32u * (uint32_t)win * 2u;
             int gen = VS_GEN_SIMPLE;
             ra.warp_bytes = tile_bytes;
-            if (b.mode != VS_MODE_FILTER && compact && amp_fits && !ctx->opt_simple_gen && t_min >= 24 && t_max <= 8192) {
+            if (b.mode != VS_MODE_FILTER && compact != VS_TAB_FULL && amp_fits && !ctx->opt_simple_gen && t_min >= 24 && t_max <= 8192) {
                 const uint32_t per_win = (uint32_t)(win / t_min) + 2u;      /* pitch periods a lane can start in one window */
                 const uint32_t ahead = 2u * per_win + 3u;
                 uint32_t R = 8;
                 while (R < ahead) R <<= 1;
                 const uint32_t cache = (sl.plan_geom[k].cache_doubles + 1u) & ~1u;
-                const uint32_t wbytes = tile_bytes + R * 256u + cache * 8u;
+                const uint32_t wbytes = tile_bytes + R * 32u * VS_TAB_ENTRY_BYTES(compact) + cache * 8u;
                 if (R <= 64 && 4u * wbytes <= (b.mode == VS_MODE_FLOW ? 100u : 200u) * 1024u) {
                     gen = VS_GEN_FAST;
                     ra.warp_bytes = wbytes; ra.ring_R = R; ra.ring_fetch = per_win + 2u; ra.ring_ahead = ahead; ra.cache_doubles = cache;

@@ -77,10 +77,21 @@ struct VsPeriod {
     int32_t  ndw;          /* NoiseDistWidth                                                      */
 };
 
-/* compact period table entry (8 B): all a batch without glottal noise and without -z needs */
+/* Period table formats (VsPlanArgs / VsRenderArgs ::compact) */
+#define VS_TAB_FULL 0      /* VsPeriod, 32 B: anything (-z, noise with large DC, period log)                        */
+#define VS_TAB_C8   1      /* VsPeriodC, 8 B: a batch without glottal noise and without -z                           */
+#define VS_TAB_N16  2      /* VsPeriodN, 16 B: glottal noise with DC <= 1 (then T4 == 0: noise on [T3, T)), no -z    */
+#define VS_TAB_ENTRY_BYTES(fmt) ((fmt) == VS_TAB_C8 ? 8u : (fmt) == VS_TAB_N16 ? 16u : 32u)
+
 struct VsPeriodC {
     float    A;            /* Amplitude                                                           */
     uint32_t T;            /* period length                                                       */
+};
+struct VsPeriodN {
+    float    A;
+    uint32_t T_np;         /* T (low 16) | random() draws of the period before its first noise draw (high 16) */
+    uint32_t T3;           /* closure instant: the period's noise samples are [T3, T)             */
+    int32_t  ndw;          /* NoiseDistWidth                                                      */
 };
 
 /* kernel launch argument blocks */
@@ -88,8 +99,8 @@ struct VsPlanArgs {
     const VsStream *streams;
     uint32_t        n_streams;
     VsChunk        *chunks;
-    void           *table;          /* VsPeriod[] or, when compact, VsPeriodC[]                   */
-    int             compact;
+    void           *table;          /* VsPeriod[], VsPeriodC[] or VsPeriodN[]                     */
+    int             compact;        /* VS_TAB_*                                                   */
     uint32_t       *rng_snap;       /* [n_chunks][32] or NULL                                     */
     uint32_t       *n_periods;      /* [n_streams]                                                */
     const double   *costab;
@@ -106,8 +117,8 @@ struct VsRenderArgs {
                                        function of blockIdx and kernel parameters only, so the coefficients are
                                        read into UNIFORM registers (DFMA R, R, UR, R)                 */
     uint32_t        n_rows;         /* rows incl. padding, multiple of VS_NT                         */
-    const void     *table;          /* VsPeriod[] or VsPeriodC[] (compact)                           */
-    int             compact;
+    const void     *table;          /* VsPeriod[], VsPeriodC[] or VsPeriodN[]                        */
+    int             compact;        /* VS_TAB_*                                                      */
     const uint32_t *n_periods;      /* [n_streams] periods the plan kernel wrote                     */
     const uint32_t *rng_snap;
     const double   *costab;

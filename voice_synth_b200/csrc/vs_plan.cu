@@ -19,6 +19,26 @@
 /* ================================================================================================
  * PLAN: one thread per stream
  * ============================================================================================== */
+/* one period into the table, in the format the render kernel asked for */
+__device__ __forceinline__ void vs_store_period(void *table, int fmt, uint64_t idx, float A, float Knew, uint32_t start, int T,
+                                                uint32_t nd, int T3, int T4, int ndw)
+{
+    if (fmt == VS_TAB_C8) {
+        VsPeriodC e;
+        e.A = A; e.T = (uint32_t)T;
+        reinterpret_cast<VsPeriodC *>(table)[idx] = e;
+    } else if (fmt == VS_TAB_N16) {
+        reinterpret_cast<uint4 *>(table)[idx] = make_uint4(__float_as_uint(A), (uint32_t)T | (nd << 16), (uint32_t)T3, (uint32_t)ndw);
+    } else {
+        VsPeriod e;
+        e.Ad = (double)A; e.Kd = (double)Knew; e.start = start;
+        e.T_np = (uint32_t)T | (nd << 16);
+        e.T34 = (uint32_t)T3 | ((uint32_t)T4 << 16);
+        e.ndw = ndw;
+        reinterpret_cast<VsPeriod *>(table)[idx] = e;
+    }
+}
+
 template <bool LOG>
 __global__ void __launch_bounds__(VS_PLAN_NT, 1) vs_plan_kernel(const VsPlanArgs a)
 {
@@ -50,8 +70,6 @@ __global__ void __launch_bounds__(VS_PLAN_NT, 1) vs_plan_kernel(const VsPlanArgs
     int T = P, T4 = 0, ndw = 0;
     float dper = 0.0f, dsh = 0.0f;
     uint32_t count = 0, np = 0, next_c = 0;
-    VsPeriod *tab = reinterpret_cast<VsPeriod *>(a.table) + st.tab_off;
-    VsPeriodC *tabc = reinterpret_cast<VsPeriodC *>(a.table) + st.tab_off;
     VsChunk *chunks = a.chunks + st.chunk0;
     uint32_t next_target = st.n_chunks ? chunks[0].gen_target : 0xffffffffu;
     vs_period_rec *log = LOG ? (vs_period_rec *)a.log + st.log_off : nullptr;
@@ -159,18 +177,7 @@ __global__ void __launch_bounds__(VS_PLAN_NT, 1) vs_plan_kernel(const VsPlanArgs
             atomicExch(a.status, np >= st.tab_cap ? VS_ENOMEM : VS_ERANGE);
             return;
         }
-        if (a.compact) {
-            VsPeriodC e;
-            e.A = A; e.T = (uint32_t)T;
-            tabc[np] = e;
-        } else {
-            VsPeriod e;
-            e.Ad = (double)A; e.Kd = (double)Knew; e.start = count;
-            e.T_np = (uint32_t)T | (nd << 16);
-            e.T34 = (uint32_t)T3 | ((uint32_t)T4 << 16);
-            e.ndw = ndw;
-            tab[np] = e;
-        }
+        vs_store_period(a.table, a.compact, st.tab_off + np, A, Knew, count, T, nd, T3, T4, ndw);
         if (LOG) {
             vs_period_rec r;
             r.T = T; r.T2 = T2; r.T3 = T3; r.T4 = T4; r.A = A; r.Knew = Knew; r.S = S;
@@ -330,8 +337,6 @@ __global__ void __launch_bounds__(VS_PLANW_NT) vs_plan_warp_kernel(const VsPlanA
     int T = P, T4 = 0, ndw = 0;
     float dper = 0.0f, dsh = 0.0f;
     uint32_t count = 0, np = 0, next_c = 0;
-    VsPeriod *tab = reinterpret_cast<VsPeriod *>(a.table) + st.tab_off;
-    VsPeriodC *tabc = reinterpret_cast<VsPeriodC *>(a.table) + st.tab_off;
     VsChunk *chunks = a.chunks + st.chunk0;
     uint32_t next_target = st.n_chunks ? chunks[0].gen_target : 0xffffffffu;
     /* the target after that is fetched one mark ahead: a single long stream crosses a chunk start every few
@@ -367,20 +372,7 @@ __global__ void __launch_bounds__(VS_PLANW_NT) vs_plan_warp_kernel(const VsPlanA
                     next_target = after_target;
                     after_target = next_c + 1 < st.n_chunks ? chunks[next_c + 1].gen_target : 0xffffffffu;
                 }
-                if (lane == 0) {
-                    if (a.compact) {
-                        VsPeriodC e;
-                        e.A = An; e.T = (uint32_t)T;
-                        tabc[np] = e;
-                    } else {
-                        VsPeriod e;
-                        e.Ad = (double)An; e.Kd = (double)kn[pk]; e.start = count;
-                        e.T_np = (uint32_t)T | (3u << 16);
-                        e.T34 = (uint32_t)(2 * T2);
-                        e.ndw = 0;
-                        tab[np] = e;
-                    }
-                }
+                if (lane == 0) vs_store_period(a.table, a.compact, st.tab_off + np, An, kn[pk], count, T, 3u, 2 * T2, 0, 0);
                 count += (uint32_t)T;
                 np++;
             }
@@ -521,20 +513,7 @@ __global__ void __launch_bounds__(VS_PLANW_NT) vs_plan_warp_kernel(const VsPlanA
             atomicExch(a.status, np >= st.tab_cap ? VS_ENOMEM : VS_ERANGE);
             return;
         }
-        if (lane == 0) {
-            if (a.compact) {
-                VsPeriodC e;
-                e.A = A; e.T = (uint32_t)T;
-                tabc[np] = e;
-            } else {
-                VsPeriod e;
-                e.Ad = (double)A; e.Kd = (double)Knew; e.start = count;
-                e.T_np = (uint32_t)T | (nd << 16);
-                e.T34 = (uint32_t)T3 | ((uint32_t)T4 << 16);
-                e.ndw = ndw;
-                tab[np] = e;
-            }
-        }
+        if (lane == 0) vs_store_period(a.table, a.compact, st.tab_off + np, A, Knew, count, T, nd, T3, T4, ndw);
         count += (uint32_t)T;                                             /* :413 */
         np++;
     } while (count < st.n);                                               /* :423 */

@@ -44,6 +44,12 @@ __device__ __forceinline__ void vs_cp_async8(uint32_t dst_smem, const void *src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
 }
+template <uint32_t BYTES>
+__device__ __forceinline__ void vs_cp_async(uint32_t dst_smem, const void *src)
+{
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
+}
 __device__ __forceinline__ void vs_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 /* this thread's shared-memory writes become visible to the async proxy (the TMA engine) */
 __device__ __forceinline__ void vs_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -60,8 +66,8 @@ __device__ __forceinline__ void vs_bulk_wait_read() { asm volatile("cp.async.bul
  * check around every breakpoint: tests/tools/noisecheck.c). */
 __device__ __forceinline__ int vs_noise_w2(int32_t r, double ndwd)
 {
-    double t = __fma_rn((double)r, VS_INV_RM, -0.5);
-    if (r == 2147483647) t = 0.5;
+    /* r == M would have to give t = 1/2 exactly; r = M-1 gives 1/2 - 5e-10, the same ceiling for NDW < 2^19 */
+    const double t = __fma_rn((double)min(r, 2147483646), VS_INV_RM, -0.5);
     return vs_ceil_s16(__dmul_rn(t, ndwd));
 }
 
@@ -159,7 +165,6 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
     constexpr bool HASGEN = MODE != VS_MODE_FILTER, HASFILT = MODE != VS_MODE_FLOW;
     constexpr bool FAST = HASGEN && GEN == VS_GEN_FAST;
     static_assert((WIN % VS_RING) == 0 && ((WIN / VS_RING) & 1) == 1, "window = odd number of ring blocks");
-    static_assert(!(FAST && NOISE), "the fast generator has no noise path");
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     /* Roles.  Rows come in groups of 32 ("pairs"); pair p of a CTA is served by warp p+4, the FILTER warp (F), and
@@ -178,7 +183,7 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
     /* shared memory: per pair [NT tiles | period ring | pulse-table cache | row descriptors], then the CTA's RNG states */
     const uint32_t tile_off = (uint32_t)pair * a.warp_bytes;
     const uint32_t ring_off = tile_off + (uint32_t)NT * TILE;
-    const uint32_t cache_off = ring_off + a.ring_R * 256u;
+    const uint32_t cache_off = ring_off + a.ring_R * (32u * ((GEN == VS_GEN_FAST && NOISE && MODE != VS_MODE_FILTER) ? 16u : 8u));
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
     uint32_t *s_rng = reinterpret_cast<uint32_t *>(smem + 4u * a.warp_bytes);      /* [31][VS_NT], NOISE only */
 
@@ -239,7 +244,7 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
     bool nz = false;
     const unsigned char *ptab = nullptr;                    /* the row's period table */
     if (HASGEN && active) {
-        ptab = reinterpret_cast<const unsigned char *>(a.table) + st->tab_off * (a.compact ? sizeof(VsPeriodC) : sizeof(VsPeriod));
+        ptab = reinterpret_cast<const unsigned char *>(a.table) + st->tab_off * VS_TAB_ENTRY_BYTES(a.compact);
         T2 = st->T2;
         DCi = (int)ceilf(st->DC);                           /* (float)x < DC  <=>  x < ceil(DC) for integer x */
         DCs = st->DCs;
@@ -254,6 +259,13 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
      * row's last period it keeps running on periods of amplitude 0 and length tpad (never stored) */
     const int tpad = (HASGEN && active) ? (int)st->tpad : VS_GROUP;
     int ic = 0, Tc = nstart - blk0, Tn = tpad;
+    /* ... with glottal noise (VsPeriodN entries): closure instants, noise widths, draws to skip; the generator
+     * state as the slot it will overwrite next (byte offset into the lane's column) and its last three values */
+    constexpr uint32_t EB = (FAST && NOISE) ? 16u : 8u;     /* ring entry bytes */
+    int T3c = VS_BIG_T, T3n = VS_BIG_T, npn = 0, skip = 0;
+    double ndwc = 0.0;
+    int ndwn = 0;
+    uint32_t rf = 3u * VS_NT * 4u, r1 = 0, r2 = 0, r3 = 0;
     double Adc = 0.0;
     float An = 0.0f;
     uint32_t tb = cache_off;                                /* the row's pulse table in shared memory (byte offset) */
@@ -305,18 +317,26 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
         if (active) {
             const uint32_t want = min((uint32_t)q0 + a.ring_ahead, (uint32_t)nper);
             for (; qf < want; qf++)
-                vs_cp_async8(smem_base + ring_off + ((qf & Rm) * 32u + lane) * 8u, ptab + (size_t)qf * sizeof(VsPeriodC));
+                vs_cp_async<EB>(smem_base + ring_off + ((qf & Rm) * 32u + lane) * EB, ptab + (size_t)qf * EB);
         }
         vs_cp_async_wait_all();
         __syncwarp();
         if (active && q0 <= qlast) {
-            const uint2 e = *reinterpret_cast<const uint2 *>(smem + ring_off + (((uint32_t)q0 & Rm) * 32u + lane) * 8u);
-            An = __uint_as_float(e.x); Tn = (int)e.y;
+            if (NOISE) {
+                const uint4 e = *reinterpret_cast<const uint4 *>(smem + ring_off + (((uint32_t)q0 & Rm) * 32u + lane) * EB);
+                An = __uint_as_float(e.x); Tn = (int)(e.y & 0xffffu); T3n = (int)e.z; ndwn = (int)e.w;
+                npn = 0;                                    /* the chunk's first period: its perturbation draws are behind the snapshot */
+            } else {
+                const uint2 e = *reinterpret_cast<const uint2 *>(smem + ring_off + (((uint32_t)q0 & Rm) * 32u + lane) * EB);
+                An = __uint_as_float(e.x); Tn = (int)e.y;
+            }
         }
     }
     if (NOISE && HASGEN && active && nz) {
-        /* the plan kernel's snapshot is taken after the first period's K draw; it is stored with f = 3 */
+        /* the plan kernel's snapshot is taken after the first period's K draw; it is stored with f = 3:
+         * word 3 is the oldest value r[n-31], words 0..2 are r[n-3], r[n-2], r[n-1] */
         for (int k = 0; k < VS_RNG_DEG; k++) rng.r[k * VS_NT] = __ldg(a.rng_snap + (size_t)chunk_id * 32 + k);
+        r3 = rng.r[0]; r2 = rng.r[VS_NT]; r1 = rng.r[2 * VS_NT];
     }
     const int16_t *fin = (MODE == VS_MODE_FILTER && active) ? a.flow_in + st->in_off : nullptr;
 
@@ -331,22 +351,72 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
         const int icT = ic - Tc;
         const double Adn = (double)An;
         const unsigned char *bc = smem + tb + (uint32_t)ic * 8u, *bn = smem + tb + icT * 8;   /* table entry of sample 0 in the current / next period */
+        /* glottal noise (flowgen_shimmer.c:385-399 with T4 == 0): the samples from the closure instant T3 to the
+         * period's end each take one random() value.  Bit u of nm: sample u is one of them. */
+        uint32_t nm = 0;
+        double ndwn_d = 0.0;
+        if (NOISE) {
+            auto low = [](int k) -> uint32_t { return (1u << min(max(k, 0), VS_GROUP)) - 1u; };     /* bits [0, k) */
+            const uint32_t lk = low(-icT);                                                           /* samples of the current period */
+            nm = nz ? ((~low(T3c - ic) & lk) | (~low(T3n - icT) & ~lk)) & 0xffu : 0u;
+            ndwn_d = (double)ndwn;
+        }
+        unsigned char *rcol = reinterpret_cast<unsigned char *>(rng.r);
 #pragma unroll
         for (int u = 0; u < VS_GROUP; u++) {
             const bool nx = icT + u >= 0;                   /* the sample belongs to the next period */
             const double fac = *reinterpret_cast<const double *>((nx ? bn : bc) + u * 8);
             const double A = nx ? Adn : Adc;
             const int v = __double2int_ru(__dmul_rn(A, fac));
-            x[u] = max(v, first ? (nx ? DCs : 0) : DCs);
+            int xv = max(v, first ? (nx ? DCs : 0) : DCs);
+            if (NOISE) {
+                /* glibc random(): r[n] = r[n-31] + r[n-3]; the slot of r[n-31] takes r[n].  Branch free: every lane
+                 * computes the value, a lane that does not draw writes its slot's old content back.  A draw is
+                 * a noise sample (bit u of nm) or one of the period's perturbation draws still to be stepped over
+                 * (`skip`; they are used up before the period's first noise sample at T3 >= 16) */
+                const bool ns = ((nm >> u) & 1u) != 0u;
+                const bool dr = ns || skip > 0;
+                skip = max(skip - 1, 0);
+                const uint32_t old = *reinterpret_cast<const uint32_t *>(rcol + rf);
+                const uint32_t val = old + r3;
+                *reinterpret_cast<uint32_t *>(rcol + rf) = dr ? val : old;
+                const uint32_t rfn = rf + VS_NT * 4u == VS_RNG_DEG * VS_NT * 4u ? 0u : rf + VS_NT * 4u;
+                rf = dr ? rfn : rf;
+                r3 = dr ? r2 : r3; r2 = dr ? r1 : r2; r1 = dr ? val : r1;
+                const int w = vs_noise_w2((int32_t)(val >> 1), nx ? ndwn_d : ndwc);
+                xv = ns ? vs_add_clip(xv, w) : xv;
+            }
+            x[u] = xv;
         }
         /* the group's last sample may have been the period's last: promote `next`, read the entry after it */
         const bool pr = icT + VS_GROUP >= 0;
         ic += VS_GROUP;
         if (pr) { ic -= Tc; Adc = Adn; Tc = Tn; q++; }
-        const uint2 e = *reinterpret_cast<const uint2 *>(smem + ring_off + ((((uint32_t)(q + 1)) & Rm) * 32u + lane) * 8u);
         const bool valid = q < qlast;
-        An = valid ? __uint_as_float(e.x) : 0.0f;
-        Tn = valid ? (int)e.y : tpad;
+        if (NOISE) {
+            /* the promoted period's jitter / shimmer / K draws come before its noise draws (:283,:298,:325); none of
+             * its noise samples lie in this group or in the first half of the next (T3 >= T2 >= 16) */
+            if (pr) { T3c = T3n; ndwc = ndwn_d; skip = nz ? npn : 0; }
+            while (__any_sync(VS_FULL, skip > 4)) {         /* rejection-heavy streams only: the next group's first samples take four */
+                const uint32_t val = *reinterpret_cast<const uint32_t *>(rcol + rf) + r3;
+                if (skip > 4) {
+                    *reinterpret_cast<uint32_t *>(rcol + rf) = val;
+                    rf = rf + VS_NT * 4u == VS_RNG_DEG * VS_NT * 4u ? 0u : rf + VS_NT * 4u;
+                    r3 = r2; r2 = r1; r1 = val;
+                    skip--;
+                }
+            }
+            const uint4 e = *reinterpret_cast<const uint4 *>(smem + ring_off + ((((uint32_t)(q + 1)) & Rm) * 32u + lane) * EB);
+            An = valid ? __uint_as_float(e.x) : 0.0f;
+            Tn = valid ? (int)(e.y & 0xffffu) : tpad;
+            npn = valid ? (int)(e.y >> 16) : 0;
+            T3n = valid ? (int)e.z : VS_BIG_T;
+            ndwn = valid ? (int)e.w : 0;
+        } else {
+            const uint2 e = *reinterpret_cast<const uint2 *>(smem + ring_off + ((((uint32_t)(q + 1)) & Rm) * 32u + lane) * EB);
+            An = valid ? __uint_as_float(e.x) : 0.0f;
+            Tn = valid ? (int)e.y : tpad;
+        }
     };
 
     /* keep the ring `ring_ahead` periods ahead of the current one (called once per window) */
@@ -355,7 +425,7 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
         const uint32_t want = min((uint32_t)(q + 1) + a.ring_ahead, (uint32_t)max(nper, 0));
         for (uint32_t k = 0; k < a.ring_fetch; k++) {
             const uint32_t idx = qf + k;
-            if (idx < want) vs_cp_async8(smem_base + ring_off + ((idx & Rm) * 32u + lane) * 8u, ptab + (size_t)idx * sizeof(VsPeriodC));
+            if (idx < want) vs_cp_async<EB>(smem_base + ring_off + ((idx & Rm) * 32u + lane) * EB, ptab + (size_t)idx * EB);
         }
         qf = max(qf, min(want, qf + a.ring_fetch));
     };
@@ -368,9 +438,15 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
             if (q > qlast) { sT = VS_BIG_T; snopen = 0; sAd = 0.0; break; }
             dcs_cur = DCs;
             float A;
-            if (a.compact) {
+            if (a.compact == VS_TAB_C8) {
                 const uint2 e = __ldg(reinterpret_cast<const uint2 *>(ptab) + q);           /* VsPeriodC */
                 A = __uint_as_float(e.x); sT = (int)e.y;
+            } else if (a.compact == VS_TAB_N16) {
+                const uint4 e = __ldg(reinterpret_cast<const uint4 *>(ptab) + q);           /* VsPeriodN: T4 == 0 */
+                A = __uint_as_float(e.x); sT = (int)(e.y & 0xffffu); snpert = (int)(e.y >> 16);
+                sT3 = (int)e.z; sT4 = 0; sndwd = (double)(int)e.w;
+                if (NOISE && nz && q != q0)
+                    for (int k = 0; k < snpert; k++) (void)vs_rng_next<VS_NT>(rng);
             } else {
                 const VsPeriod *e = reinterpret_cast<const VsPeriod *>(ptab) + q;
                 const double2 ak = __ldg(reinterpret_cast<const double2 *>(e));
@@ -545,9 +621,9 @@ cudaError_t vs_launch_render(const VsRenderArgs &a, int mode, int gen, bool nois
 {
     if (mode == VS_MODE_FILTER) return vs_go_filt<VS_MODE_FILTER, VS_GEN_SIMPLE, false>(a, filt, s);
     if (mode == VS_MODE_FLOW) {
-        if (gen == VS_GEN_FAST && !noise) return vs_go<VS_MODE_FLOW, VS_GEN_FAST, false, VS_FILT_FMA, false>(a, s);
+        if (gen == VS_GEN_FAST) return noise ? vs_go<VS_MODE_FLOW, VS_GEN_FAST, true, VS_FILT_FMA, false>(a, s) : vs_go<VS_MODE_FLOW, VS_GEN_FAST, false, VS_FILT_FMA, false>(a, s);
         return noise ? vs_go<VS_MODE_FLOW, VS_GEN_SIMPLE, true, VS_FILT_FMA, false>(a, s) : vs_go<VS_MODE_FLOW, VS_GEN_SIMPLE, false, VS_FILT_FMA, false>(a, s);
     }
-    if (gen == VS_GEN_FAST && !noise) return vs_go_filt<VS_MODE_SYNTH, VS_GEN_FAST, false>(a, filt, s);
+    if (gen == VS_GEN_FAST) return noise ? vs_go_filt<VS_MODE_SYNTH, VS_GEN_FAST, true>(a, filt, s) : vs_go_filt<VS_MODE_SYNTH, VS_GEN_FAST, false>(a, filt, s);
     return noise ? vs_go_filt<VS_MODE_SYNTH, VS_GEN_SIMPLE, true>(a, filt, s) : vs_go_filt<VS_MODE_SYNTH, VS_GEN_SIMPLE, false>(a, filt, s);
 }
