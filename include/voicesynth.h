@@ -112,6 +112,9 @@ typedef struct vs_timing {
     uint64_t warmup_samples;  /* extra samples filtered only to settle chunk carries     */
     uint64_t h2d_bytes;       /* host->device bytes the call copied (descriptors, tables, flow_in) */
     uint64_t d2h_bytes;       /* device->host bytes the call copied (PCM, raw, period log)         */
+    uint32_t render_path;     /* which render kernel ran (last launch): bit 0 = branch-free generator, bit 1 = glottal-noise
+                                 variant, bits 2-3 = filter arithmetic (0 integer pre-emphasis, 1 FMA, 2 exact)       */
+    uint32_t reserved;
 } vs_timing;
 
 /* ---- options (vs_ctx_set_option) ------------------------------------------------------------ */

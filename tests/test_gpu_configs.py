@@ -43,17 +43,41 @@ def _check_sample(oracle, vs, p, f, pcm, offs, ns, idx, flow=None, foffs=None):
     return worst
 
 
+def _check_all(oracle, vs, p, f, pcm, offs, ns, flow=None, foffs=None, label=""):
+    """EVERY stream of the batch against the oracle, on all host cores (the oracle is a ctypes library: the GIL is
+    released inside it).  Flow bit-exact, PCM within 1 LSB; returns (streams, samples, samples off by one LSB)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(i):
+        oflow = oracle.flowgen(_opar(oracle, vs, p, i))
+        flow_ok = True if flow is None else bool(np.array_equal(flow[int(foffs[i]): int(foffs[i]) + int(ns[i])], oflow))
+        want = oracle.vowel(oflow, chr(f.preset[i]), gain=float(f.gain[i]), pre=float(f.pre[i]))
+        got = pcm[int(offs[i]): int(offs[i]) + int(ns[i])]
+        d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        return flow_ok, int(d.max()), int((d > 0).sum()), int(d.size)
+
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        res = list(ex.map(one, range(p.n), chunksize=16))
+    bad_flow = [i for i, r in enumerate(res) if not r[0]]
+    bad_pcm = [(i, r[1]) for i, r in enumerate(res) if r[1] > 1]
+    assert not bad_flow, f"{label}: flow differs from the oracle in streams {bad_flow[:10]} ({len(bad_flow)} in all)"
+    assert not bad_pcm, f"{label}: PCM more than 1 LSB off in streams {bad_pcm[:10]} ({len(bad_pcm)} in all)"
+    ones, total = sum(r[2] for r in res), sum(r[3] for r in res)
+    print(f"{label}: {p.n} streams, {total} samples checked against the oracle, {ones} samples differ by 1 LSB")
+    return p.n, total, ones
+
+
 def test_cfg2_full_batch(ctx, vs, oracle):
-    """4096 streams x 1 s, every preset, fused kernel, auto chunking (the bench workload)"""
+    """4096 streams x 1 s, every preset, fused kernel, auto chunking (the bench workload): every stream checked"""
     from voice_synth_b200 import workloads
     p, f = workloads.cfg2()
     pcm, offs, ns = ctx.synth_batch(p, f)
     t = ctx.timing()
     assert t["samples"] == 4096 * 22050 and t["chunks"] > 4096
+    assert t["render_path"] & 1, "the bench workload must run on the branch-free generator"
     flow, foffs, _ = ctx.flowgen_batch(p)
-    rng = np.random.default_rng(2)
-    idx = sorted(set(rng.integers(0, p.n, 40).tolist()) | {0, 1, 4095})
-    _check_sample(oracle, vs, p, f, pcm, offs, ns, idx, flow, foffs)
+    _check_all(oracle, vs, p, f, pcm, offs, ns, flow, foffs, label="cfg2")
     # idempotence: the same call again gives the same bytes
     pcm2, _, _ = ctx.synth_batch(p, f)
     assert np.array_equal(pcm, pcm2)
@@ -78,10 +102,9 @@ def test_cfg3_noise_grid_shard(ctx, vs, oracle):
     p, f = workloads.cfg3(n=8192, first=3 * 8192)
     pcm, offs, ns = ctx.synth_batch(p, f)
     assert int(ns.sum()) == 8192 * 44100
+    assert ctx.timing()["render_path"] & 3 == 3, "cfg3 must run on the branch-free generator with in-lane noise"
     flow, foffs, _ = ctx.flowgen_batch(p)
-    rng = np.random.default_rng(3)
-    idx = sorted(set(rng.integers(0, p.n, 24).tolist()) | {0, 8191})
-    _check_sample(oracle, vs, p, f, pcm, offs, ns, idx, flow, foffs)
+    _check_all(oracle, vs, p, f, pcm, offs, ns, flow, foffs, label="cfg3 shard")
 
 
 def test_cfg4_ten_minute_stream(ctx, vs, oracle):
@@ -108,9 +131,90 @@ def test_cfg5_corpus_slice(ctx, vs, oracle):
     from voice_synth_b200 import workloads
     p, f = workloads.cfg5(n=16384, first=500000)
     pcm, offs, ns = ctx.synth_batch(p, f)
-    rng = np.random.default_rng(5)
-    idx = sorted(set(rng.integers(0, p.n, 24).tolist()))
-    _check_sample(oracle, vs, p, f, pcm, offs, ns, idx)
+    flow, foffs, _ = ctx.flowgen_batch(p)
+    _check_all(oracle, vs, p, f, pcm, offs, ns, flow, foffs, label="cfg5 slice")
+
+
+def test_every_preset_through_one_two_and_five_chunks(ctx, vs, oracle):
+    """the ten presets x chunk classes grid: each vowel filtered as one row, as two and as five time-chunks (carry
+    warm-up differs per preset), fused and filter-only, against the oracle's waveform before and after quantisation"""
+    n = 10
+    p = vs.FlowParams.from_cli(["-d 1 -f 120 -j 1 -s 3"] * n, list(range(100, 100 + n)))
+    f = vs.FilterParams(n, "aiu1234567")
+    want = []
+    for i in range(n):
+        oflow = oracle.flowgen(_opar(oracle, vs, p, i))
+        want.append((oflow,) + tuple(oracle.vowel(oflow, chr(f.preset[i]), want_raw=True)))
+    for chunks, L in ((1, -1), (2, 11032), (5, 4416)):
+        ctx.set_option(vs.OPT_CHUNK_SAMPLES, L)
+        try:
+            pcm, offs, ns, raw = ctx.synth_batch(p, f, want_raw=True)
+            assert ctx.timing()["chunks"] == n * chunks
+            pcm2, offs2, ns2 = ctx.synth_batch(p, f)                       # without raw output: integer pre-emphasis path
+            flow_all = np.concatenate([w[0] for w in want])
+            fout, foffs, fraw = ctx.vowel_filter_batch(flow_all, ns, f, in_offsets=np.arange(n, dtype=np.uint64) * 22050, want_raw=True)
+        finally:
+            ctx.set_option(vs.OPT_CHUNK_SAMPLES, 0)
+        for i in range(n):
+            oflow, opcm, oraw = want[i]
+            for name, got, graw, o in (("fused", pcm, raw, offs), ("fused/int", pcm2, None, offs2), ("filter", fout, fraw, foffs)):
+                sl = slice(int(o[i]), int(o[i]) + 22050)
+                d = int(np.abs(got[sl].astype(np.int32) - opcm.astype(np.int32)).max())
+                assert d <= 1, f"preset {chr(f.preset[i])}, {chunks} chunk(s), {name}: {d} LSB"
+                if graw is not None:
+                    e = float(np.abs(graw[sl] - oraw).max())
+                    assert e <= 1e-5, f"preset {chr(f.preset[i])}, {chunks} chunk(s), {name}: pre-quantisation error {e}"
+
+
+def test_fast_paths_fuzz(ctx, vs, oracle):
+    """random voices inside the domain of the branch-free generator (no -z, noise without -l, default gain and
+    pre-emphasis so that both commute to the integer input), with and without glottal noise, chunked and not:
+    every stream against the oracle"""
+    rng = np.random.default_rng(77)
+    for noisy in (False, True):
+        n = 200
+        args, seeds = [], []
+        for i in range(n):
+            f0 = float(rng.uniform(75, 300))
+            a = ["-d", f"{rng.uniform(0.5, 1.2):.3f}", "-f", f"{f0:.2f}", "-g", f"{f0 + 20:.2f}"]
+            if rng.random() < 0.85:
+                a += ["-j", f"{rng.uniform(0, 4):.2f}"]
+            if rng.random() < 0.85:
+                a += ["-s", f"{rng.uniform(0, 12):.2f}"]
+            if noisy and rng.random() < 0.7:
+                a += ["-n", f"{rng.uniform(5, 45):.1f}"]
+            if rng.random() < 0.4:
+                a += ["-c", f"{rng.uniform(0.4, 0.9):.3f}"]
+            if rng.random() < 0.4:
+                a += ["-k", f"{rng.uniform(0.5, 2):.3f}"]
+            if rng.random() < 0.4:
+                a += ["-a", str(int(rng.integers(2000, 18000)))]
+            args.append(a)
+            seeds.append(int(rng.integers(0, 2**32)))
+        p = vs.FlowParams.from_cli(args, seeds)
+        f = vs.FilterParams(n)
+        f.preset[...] = [ord("aiu1234567"[int(k)]) for k in rng.integers(0, 10, n)]
+        f.gain[...] = rng.integers(1, 15, n).astype(np.float32)
+        for chunk in (0, 2048):
+            ctx.set_option(vs.OPT_CHUNK_SAMPLES, chunk)
+            try:
+                flow, foffs, ns = ctx.flowgen_batch(p)
+                pcm, offs, _ = ctx.synth_batch(p, f)
+                t = ctx.timing()
+            finally:
+                ctx.set_option(vs.OPT_CHUNK_SAMPLES, 0)
+            assert t["render_path"] & 1 and bool(t["render_path"] & 2) == noisy and (t["render_path"] >> 2) & 3 == 0
+            _check_all(oracle, vs, p, f, pcm, offs, ns, flow, foffs, label=f"fast fuzz noise={noisy} chunk={chunk}")
+            # the general generator must agree bit for bit on the flow and within 1 LSB on the PCM
+            ctx.set_option(vs.OPT_SIMPLE_GEN, 1)
+            try:
+                flow2, _, _ = ctx.flowgen_batch(p)
+                pcm2, _, _ = ctx.synth_batch(p, f)
+                assert not ctx.timing()["render_path"] & 1
+            finally:
+                ctx.set_option(vs.OPT_SIMPLE_GEN, 0)
+            assert np.array_equal(flow, flow2)
+            assert int(np.abs(pcm.astype(np.int32) - pcm2.astype(np.int32)).max()) <= 1
 
 
 def test_edge_shapes(ctx, vs, oracle):

@@ -26,7 +26,8 @@ class PeriodLogC(C.Structure):
 class TimingC(C.Structure):
     _fields_ = [("plan_ms", C.c_float), ("render_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_uint32),
                 ("chunks", C.c_uint32), ("samples", C.c_uint64), ("warmup_samples", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("render_path", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 _lib = None

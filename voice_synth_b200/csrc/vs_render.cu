@@ -282,9 +282,12 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
     /* A above 32767: x[T2] = (short)ceil(A) < 0, the falling branch is left at once (flowgen_shimmer.c:329) */
     auto nopen_of = [&](float A, int T) -> int { return min(T, A > 32767.0f ? T2 : 2 * T2); };
 
+    /* Do the pulse tables of this warp's rows fit the pair's cache?  Nearly always (the host sorts rows by table and
+     * sizes the cache for the typical warp); a warp with too many distinct tables -- the odd one that collects the
+     * first or last chunks of many voices -- falls back to the general generator for its 32 rows. */
+    bool wfast = FAST;
     if (FAST) {
-        /* pulse tables into the pair's cache: one copy per distinct table of the warp's rows (the host sized the
-         * cache from the same row order, so everything fits) */
+        /* pulse tables into the pair's cache: one copy per distinct table of the warp's rows */
         const uint32_t key = active ? pulse_off : 0xffffffffu;
         const uint32_t grp = __match_any_sync(VS_FULL, key);
         const int leader = __ffs((int)grp) - 1;
@@ -300,28 +303,27 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
         }
         const uint32_t base = incl - mine;
         const uint32_t lbase = __shfl_sync(VS_FULL, base, leader);
-        uint32_t leaders = __ballot_sync(VS_FULL, mine > 0u);
+        wfast = __shfl_sync(VS_FULL, incl, 31) <= a.cache_doubles;
+        uint32_t leaders = wfast ? __ballot_sync(VS_FULL, mine > 0u) : 0u;
         double *cache = reinterpret_cast<double *>(smem + cache_off);
         while (leaders) {
             const int L = __ffs((int)leaders) - 1;
             leaders &= leaders - 1u;
             const uint32_t src = __shfl_sync(VS_FULL, pulse_off, L), n = __shfl_sync(VS_FULL, len, L), dst = __shfl_sync(VS_FULL, base, L);
             const uint32_t np = __shfl_sync(VS_FULL, mine, L);
-            if (dst + np <= a.cache_doubles)
-                for (uint32_t k = lane; k < np; k += 32) cache[dst + k] = k < n ? __ldg(a.costab + src + k) : 0.0;
-            else if (lane == 0) atomicExch(a.status, VS_ECUDA);
+            for (uint32_t k = lane; k < np; k += 32) cache[dst + k] = k < n ? __ldg(a.costab + src + k) : 0.0;
         }
         tb = cache_off + lbase * 8u;
         /* first entries of the period ring, then the first period as `next` of an empty current period that
          * covers the slots before the row's first sample */
-        if (active) {
+        if (active && wfast) {
             const uint32_t want = min((uint32_t)q0 + a.ring_ahead, (uint32_t)nper);
             for (; qf < want; qf++)
                 vs_cp_async<EB>(smem_base + ring_off + ((qf & Rm) * 32u + lane) * EB, ptab + (size_t)qf * EB);
         }
         vs_cp_async_wait_all();
         __syncwarp();
-        if (active && q0 <= qlast) {
+        if (active && wfast && q0 <= qlast) {
             if (NOISE) {
                 const uint4 e = *reinterpret_cast<const uint4 *>(smem + ring_off + (((uint32_t)q0 & Rm) * 32u + lane) * EB);
                 An = __uint_as_float(e.x); Tn = (int)(e.y & 0xffffu); T3n = (int)e.z; ndwn = (int)e.w;
@@ -508,11 +510,11 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
             return;
         }
         unsigned char *trow = tbase + (uint32_t)lane * TSB;
-        if (FAST) ring_refill();
+        if (FAST && wfast) ring_refill();
 #pragma unroll 1
         for (int g = 0; g < NGRP; g++) {
             int x[VS_GROUP];
-            if (FAST) {
+            if (FAST && wfast) {
                 if (w == 0 && g == 0) gen_fast(x, true);
                 else gen_fast(x, false);
             } else {
