@@ -45,33 +45,35 @@ def _ref_tools():
 
 
 def _run_ref_stream(job):
-    ref, tmpdir, idx, fargs, preset, seed = job
+    ref, tmpdir, idx, fargs, preset, seed, suffix = job
     env = dict(os.environ, VS_SEED=str(seed), LD_PRELOAD=str(ref / "timeshim.so"))
-    f = os.path.join(tmpdir, f"f{idx}.wav")
-    o = os.path.join(tmpdir, f"o{idx}.wav")
-    subprocess.run([str(ref / "flowgen_shimmer"), "-o", f] + fargs, env=env, stdout=subprocess.DEVNULL, check=True)
-    subprocess.run([str(ref / "vowel"), "-i", f, "-o", o, "-v", preset], env=env, stdout=subprocess.DEVNULL, check=True)
-    n = (os.path.getsize(o) - 72) // 2
-    os.unlink(f)
-    os.unlink(o)
+    # file names relative to the scratch directory: the tools strcpy() them into char[30] (flowgen_shimmer.c:143-146)
+    f, o = f"f{idx}.wav", f"o{idx}.wav"
+    subprocess.run([str(ref / ("flowgen_shimmer" + suffix)), "-o", f] + fargs, env=env, cwd=tmpdir, stdout=subprocess.DEVNULL, check=True)
+    subprocess.run([str(ref / ("vowel" + suffix)), "-i", f, "-o", o, "-v", preset], env=env, cwd=tmpdir, stdout=subprocess.DEVNULL, check=True)
+    n = (os.path.getsize(os.path.join(tmpdir, o)) - 72) // 2
+    os.unlink(os.path.join(tmpdir, f))
+    os.unlink(os.path.join(tmpdir, o))
     return n
 
 
 def _run_port_stream(job):
     from oracle import pyoracle as O
-    _, _, idx, fargs, preset, seed = job
+    _, _, idx, fargs, preset, seed, _ = job
     par = O.flow_par_from_cli(["-o", "x"] + fargs, seed)
     return int(O.vowel(O.flowgen(par), preset).size)
 
 
-def cpu_reference_throughput(n_streams, first=0):
-    """Msamples/s of the reference CPU pipeline over `n_streams` streams of the bench workload."""
+def cpu_reference_throughput(n_streams, first=0, o2=False):
+    """Msamples/s of the reference CPU pipeline over `n_streams` streams of the bench workload: the unmodified tools,
+    one process per core (flowgen_shimmer -> WAV on tmpfs -> vowel), built with the Makefile's flags (-O0) or -O2."""
     from voice_synth_b200 import workloads
     p, f = workloads.cfg2(n=N_STREAMS)
     ref = _ref_tools()
+    suffix = "_O2" if (o2 and ref and (ref / "vowel_O2").exists()) else ""
     cores = os.cpu_count() or 1
     tmpdir = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-    jobs = [(ref, tmpdir, i, workloads.cli_args(p, i % N_STREAMS), chr(f.preset[i % N_STREAMS]), int(p.seed[i % N_STREAMS]))
+    jobs = [(ref, tmpdir, i, workloads.cli_args(p, i % N_STREAMS), chr(f.preset[i % N_STREAMS]), int(p.seed[i % N_STREAMS]), suffix)
             for i in range(first, first + n_streams)]
     fn = _run_ref_stream if ref else _run_port_stream
     t0 = time.perf_counter()
@@ -91,12 +93,13 @@ def run_reference_arm(args, rank, world):
     per_step = args.ref_streams
     vals = []
     for it in range(args.warmup + args.steps):
-        v, cores, kind, dt, total = cpu_reference_throughput(per_step, first=it * per_step)
+        v, cores, kind, dt, total = cpu_reference_throughput(per_step, first=(it * per_step) % N_STREAMS)
         if it >= args.warmup:
             vals.append((v, dt))
     value = sum(v for v, _ in vals) / len(vals)
     ms = 1e3 * sum(d for _, d in vals) / len(vals)
-    sample = (f"{per_step} of the workload's {N_STREAMS} streams per step: flowgen_shimmer -> tmpfs WAV -> vowel, "
+    sample = (f"{per_step} of the workload's {N_STREAMS} streams per step (a rate on the same stream distribution, not the whole batch): "
+              f"flowgen_shimmer -> tmpfs WAV -> vowel, "
               f"{'unmodified reference tools built with the Makefile flags (-O0)' if kind == 'reference' else 'oracle port'}, "
               f"one process per core")
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "Msamples/s", "n_gpus": args.gpus,
@@ -162,6 +165,7 @@ def measured_peaks():
 
 
 def ncu_traffic():
+    """DRAM bytes (read + write) of ONE launch of the fused render kernel, from the committed ncu capture."""
     p = ROOT / "profiles" / "ncu_summary.json"
     if p.exists():
         try:
@@ -203,6 +207,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-streams", type=int, default=1024, help="streams per step of the reference arm")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="streams of the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--no-other", action="store_true", help="skip the cfg3 / cfg5 workloads")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -230,6 +235,12 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
 
     # the rank's share of the job: its own 4096 streams (distinct seeds), nothing is exchanged
     p, f = workloads.cfg2(n=N_STREAMS)
@@ -267,6 +278,8 @@ def main():
     t = ctx.timing()
     launches += t["launches"] * args.steps
     warm = t["warmup_samples"]
+    path = t["render_path"]
+    n_chunks = t["chunks"]
 
     # per-kernel durations (CUDA events on the launching stream, recorded by the library around the
     # plan and render launches of a call), averaged over a few more steps of the same loop
@@ -295,15 +308,90 @@ def main():
     t = ctx.timing()
     h2d, d2h = t["h2d_bytes"], t["d2h_bytes"]
     launches += t["launches"] * args.steps
+    ctx.set_option(api.OPT_ASYNC_HOST, 0)
+
+    # ---- the two stand-alone kernels on the same batch (device-resident): vs_flowgen_batch, vs_vowel_filter_batch ----
+    def best_render(fn, reps=6):
+        best = None
+        for _ in range(reps):
+            fn()
+            tt = ctx.timing()
+            if best is None or tt["render_ms"] < best["render_ms"]:
+                best = tt
+        return best
+
+    flow_dev = torch.empty(samples_per_step, dtype=torch.int16, device="cuda")
+    t_flow = best_render(lambda: ctx.flowgen_batch(p, out=flow_dev))
+    t_filt = best_render(lambda: ctx.vowel_filter_batch(flow_dev, ns, f, out=dev_out))
+    launches += (t_flow["launches"] + t_filt["launches"]) * 6
+    del flow_dev
+
+    # ---- BASELINE.json's multi-GPU configurations, this rank's share of each -------------------------
+    other = {}
+    if not args.no_other:
+        # configs[2]: 65 536 streams x 2 s, glottal noise, 8 192-stream shard per GPU; device-resident like `value`
+        p3, f3 = workloads.cfg3(n=8192, first=rank * 8192)
+        n3 = int(api.flow_nsamples(p3).sum())
+        out3 = torch.empty(n3, dtype=torch.int16, device="cuda")
+        for _ in range(3):
+            ctx.synth_batch(p3, f3, out=out3)
+        ctx.sync()
+        barrier()
+        k3 = 10
+        e0.record(stream)
+        for _ in range(k3):
+            ctx.synth_batch(p3, f3, out=out3)
+        e1.record(stream)
+        barrier()
+        ms3 = e0.elapsed_time(e1) / k3
+        t3 = ctx.timing()
+        launches += t3["launches"] * (k3 + 3)
+        del out3
+        # configs[4]: 1 M utterances x 1 s, 131 072 per GPU, PCM streamed to pinned host memory: eight calls of
+        # 16 384 utterances alternate between two pinned buffers, PCIe inside the timed region
+        sub, nsub = 16384, 8
+        parts = [workloads.cfg5(n=sub, first=(rank * nsub + k) * sub) for k in range(nsub)]
+        n5 = [int(api.flow_nsamples(pp).sum()) for pp, _ in parts]
+        ring = [torch.empty(max(n5), dtype=torch.int16).pin_memory().numpy() for _ in range(2)]
+        ctx.set_option(api.OPT_ASYNC_HOST, 1)
+
+        def sweep():
+            for k, (pp, ff) in enumerate(parts):
+                ctx.synth_batch(pp, ff, out=ring[k & 1])
+            ctx.sync()
+
+        sweep()
+        barrier()
+        t0 = time.perf_counter()
+        sweep()
+        ms5 = (time.perf_counter() - t0) * 1e3
+        barrier()
+        t5 = ctx.timing()
+        launches += t5["launches"] * nsub * 2
+        ctx.set_option(api.OPT_ASYNC_HOST, 0)
+        del ring
+        ms3, ms5 = max_over_ranks([ms3, ms5])
+        other = {
+            "cfg3": {"workload": "65 536 streams x 2 s, jitter x shimmer x F0 grid, glottal noise 20 dB: 8 192-stream shard per GPU, "
+                                 "fused vs_synth_batch, PCM resident in HBM",
+                     "value": round(n3 * world / (ms3 * 1e-3) / 1e6, 1), "unit": "Msamples/s", "ms_per_step": round(ms3, 4),
+                     "plan_ms": round(t3["plan_ms"], 4), "render_ms": round(t3["render_ms"], 4), "render_path": t3["render_path"]},
+            "cfg5": {"workload": "1 M utterances x 1 s (hashed F0 / jitter / shimmer / SNR / vowel): 131 072 per GPU as 8 calls of 16 384 "
+                                 "into two alternating pinned host buffers, PCIe inside the timed region",
+                     "value": round(sum(n5) * world / (ms5 * 1e-3) / 1e6, 1), "unit": "Msamples/s", "ms_per_sweep": round(ms5, 2),
+                     "d2h_bytes_per_sweep": int(2 * sum(n5)), "render_path": t5["render_path"]},
+        }
     clocks = sampler.stop()
 
     fp64_tflops, fp64_mhz = ctx.fp64_peak()
 
-    # max over ranks
-    times = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    # max over ranks; every rank's own e2e as well
+    e2e_all = [e2e_ms]
     if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(times[0]), float(times[1])
+        gathered = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(gathered, torch.tensor([e2e_ms], dtype=torch.float64, device="cuda"))
+        e2e_all = [float(g[0]) for g in gathered]
+    dev_ms, e2e_ms = max_over_ranks([dev_ms, e2e_ms])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -315,7 +403,16 @@ def main():
     peak, peak_src = measured_peaks()
     r_ms = float(np.mean(render_ms))
     achieved = 2.0 * samples_per_step / (r_ms * 1e-3) / 1e9            # algorithmic bytes: 2 B per output sample
-    dfma_rate = FP64_INSTR_PER_SAMPLE * (samples_per_step + warm) / (r_ms * 1e-3) / 1e12
+    # FP64-pipe instructions per sample of the kernel that ran: the recurrence's 22 FMAs (+ gain multiply and
+    # pre-emphasis FMA unless both were moved to the integer input) + the generator's one multiply
+    filt = (path >> 2) & 3
+    per_sample = {0: 22, 1: 24, 2: 46}[filt] + 1
+    peak_dfma = fp64_tflops / 2
+    issued = per_sample * (samples_per_step + warm) / (r_ms * 1e-3) / 1e12
+    useful = per_sample * samples_per_step / (r_ms * 1e-3) / 1e12
+    sm_mhz = clocks.get("sm_mhz") or 0
+    peak_at_clock = 64 * 148 * sm_mhz * 1e6 / 1e12 if sm_mhz else None   # 64 DFMA / clk / SM at the clock sampled under load
+    gen_name = "branch-free" if path & 1 else "general"
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(dev_ms, 4), "higher_is_better": True, "scaling": "weak",
@@ -324,17 +421,34 @@ def main():
                                "jitter 0-3.5 %, shimmer 0-7.5 %, fused vs_synth_batch",
                    "streams_per_gpu": N_STREAMS, "samples_per_step_per_gpu": samples_per_step,
                    "l2": "output 180.6 MB per step > 126 MB L2, rewritten every step",
-                   "plan_ms": round(float(np.mean(plan_ms)), 4), "render_ms": round(r_ms, 4)},
+                   "plan_ms": round(float(np.mean(plan_ms)), 4), "render_ms": round(r_ms, 4),
+                   "chunks": int(n_chunks), "warmup_samples_per_step": int(warm),
+                   "other_workloads": other},
         "e2e": {"value": round(e2e, 1), "unit": "Msamples/s", "ms_per_step": round(e2e_ms, 3),
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "per_rank_Msamples_s": [round(samples_per_step / (m * 1e-3) / 1e6, 1) for m in e2e_all]},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "vs_render_kernel<SYNTH> (10 per-preset launches per step)", "achieved": round(achieved, 1),
-                     "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": ncu_traffic(), "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": f"vs_render_kernel<SYNTH> ({gen_name} generator, one launch per step)",
+                     "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                     "traffic": ncu_traffic(), "peak_source": peak_src,
                      "note": "the FP64 recurrence, not HBM, binds this kernel (SURVEY.md 8d): see fp64",
-                     "fp64": {"achieved_tdfma_s": round(dfma_rate, 3), "peak_tdfma_s": round(fp64_tflops / 2, 3),
-                              "frac": round(dfma_rate / (fp64_tflops / 2), 4), "dfma_per_sample": FP64_INSTR_PER_SAMPLE,
-                              "counts": "useful + carry warm-up samples", "peak_source": "vs_measure_fp64_peak on this GPU",
-                              "implied_sm_mhz": round(fp64_mhz)}},
+                     "fp64": {"dfma_per_sample": per_sample, "peak_tdfma_s": round(peak_dfma, 3),
+                              "peak_source": "vs_measure_fp64_peak on this GPU (64 DFMA/clk/SM at the clock it implies)",
+                              "implied_sm_mhz": round(fp64_mhz),
+                              "achieved_tdfma_s": round(issued, 3), "frac": round(issued / peak_dfma, 4),
+                              "counts": "frac / achieved: useful + carry warm-up samples; frac_useful / useful_tdfma_s: output samples only",
+                              "useful_tdfma_s": round(useful, 3), "frac_useful": round(useful / peak_dfma, 4),
+                              "peak_at_sampled_clock_tdfma_s": round(peak_at_clock, 3) if peak_at_clock else None,
+                              "frac_useful_at_sampled_clock": round(useful / peak_at_clock, 4) if peak_at_clock else None}},
+        "roofline_flow": {"bound": "hbm", "kernel": "vs_render_kernel<FLOW> via vs_flowgen_batch, same batch, PCM resident in HBM",
+                          "bytes_per_sample": 2, "render_ms": round(t_flow["render_ms"], 4), "plan_ms": round(t_flow["plan_ms"], 4),
+                          "achieved": round(2.0 * samples_per_step / (t_flow["render_ms"] * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                          "frac": round(2.0 * samples_per_step / (t_flow["render_ms"] * 1e-3) / 1e9 / peak, 4)},
+        "roofline_filter": {"bound": "hbm", "kernel": "vs_render_kernel<FILTER> via vs_vowel_filter_batch, same batch, flow and PCM resident in HBM",
+                            "bytes_per_sample": 4, "render_ms": round(t_filt["render_ms"], 4),
+                            "achieved": round(4.0 * samples_per_step / (t_filt["render_ms"] * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                            "frac": round(4.0 * samples_per_step / (t_filt["render_ms"] * 1e-3) / 1e9 / peak, 4),
+                            "note": "FP64 bound like the fused kernel; warm-up samples are read again per chunk"},
         "clocks": clocks,
         "numa": numa,
     }
@@ -344,6 +458,10 @@ def main():
             line["cpu_baseline"] = {"value": round(v, 3), "unit": "Msamples/s", "cores": cores, "kind": kind,
                                     "sample": f"{args.cpu_sample} of the {N_STREAMS} streams ({total} samples, {dt:.1f} s wall): "
                                               "flowgen_shimmer -> tmpfs WAV -> vowel, one process per core, Makefile flags (-O0)"}
+            v2, _, kind2, dt2, total2 = cpu_reference_throughput(args.cpu_sample, o2=True)
+            if kind2 == "reference":
+                line["cpu_baseline"]["o2"] = {"value": round(v2, 3), "unit": "Msamples/s",
+                                              "sample": f"the same {args.cpu_sample} streams with the tools built at -O2 (bit-identical PCM), {dt2:.1f} s wall"}
         except Exception as ex:  # the baseline is a report, never a reason to lose the GPU numbers
             line["cpu_baseline"] = {"value": None, "unit": "Msamples/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
     print(json.dumps(line), flush=True)
