@@ -46,7 +46,8 @@ extern "C" {
 #define VS_ENOMEM   -4   /* host or device allocation failed                                    */
 #define VS_ECUDA    -5   /* CUDA runtime error; see vs_last_error()                             */
 #define VS_ENODEV   -6   /* no usable sm_100 device / bad device index                          */
-#define VS_EOVERLAP -7   /* output rows overlap or exceed the 2^31-1 samples/stream limit       */
+#define VS_EOVERLAP -7   /* output rows overlap each other (or, for device buffers, the filter's input), or a stream
+                            exceeds the 2^31-1 samples limit                                    */
 
 /* ---- stream flags: "the argument was given" bits the reference main loop tests -------------- */
 #define VS_F_JITTER  0x01u   /* -j given  (flowgen_shimmer.c:248: arg.jitter != -1)             */

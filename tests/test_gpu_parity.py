@@ -291,3 +291,28 @@ def _oracle_noise_only(oracle, pcm, snr_db, seed, fs):
             a = f32(float(width) * (float(nv) - 0.5))
             y[base + i] = L.vso_round2int(float(y[base + i]) + float(a))
     return y
+
+
+def test_overlapping_rows_are_refused(ctx, vs):
+    """VS_EOVERLAP: output rows that intersect (they would be written by different CTAs at once), and a filter
+    running in place on device memory (time-chunks re-read flow the previous chunk has already overwritten)"""
+    import torch
+    p = vs.FlowParams.from_cli(["-d 1 -f 120 -j 1 -s 3"] * 3, [1, 2, 3])
+    f = vs.FilterParams(3, "aiu")
+    out = np.zeros(3 * 22050, dtype=np.int16)
+    for offs in ([0, 22049, 44100], [0, 0, 22050], [100, 22050, 22000]):
+        with pytest.raises(vs.VsError) as e:
+            ctx.synth_batch(p, f, out=out, offsets=np.array(offs, dtype=np.uint64))
+        assert e.value.code == vs.VS_EOVERLAP
+    # touching rows are fine
+    pcm, _, _ = ctx.synth_batch(p, f, out=out, offsets=np.array([0, 22050, 44100], dtype=np.uint64))
+    flow = torch.zeros(3 * 22050, dtype=torch.int16, device="cuda")
+    ctx.flowgen_batch(p, out=flow)
+    ctx.sync()
+    with pytest.raises(vs.VsError) as e:
+        ctx.vowel_filter_batch(flow, [22050] * 3, f, out=flow)
+    assert e.value.code == vs.VS_EOVERLAP
+    dst = torch.zeros_like(flow)
+    ctx.vowel_filter_batch(flow, [22050] * 3, f, out=dst)
+    ctx.sync()
+    assert int((dst.cpu().numpy().astype(np.int32) - pcm.astype(np.int32)).__abs__().max()) <= 1

@@ -67,7 +67,7 @@ struct Slot {
     cudaEvent_t slab_done[2] = {nullptr, nullptr};   /* D2H of the slab using pcm[k] finished */
     cudaEvent_t slab_ready = nullptr;                /* render of the current slab finished   */
     DevBuf streams[VS_DEPTH], chunks[VS_DEPTH], order[VS_DEPTH], table[VS_DEPTH], snap[VS_DEPTH], nper[VS_DEPTH], status[VS_DEPTH];
-    DevBuf costab, coef, pcm[2], raw[2], flowin[2], log;
+    DevBuf costab, pcm[2], raw[2], flowin[2], log;
     PinBuf h_streams[VS_DEPTH], h_chunks[VS_DEPTH], h_order[VS_DEPTH], h_nper[VS_DEPTH], h_status[VS_DEPTH];
     size_t costab_uploaded = 0;
     std::vector<cudaEvent_t> tev;                    /* timing events (slot 0 only) */
@@ -129,6 +129,13 @@ struct vs_ctx {
 };
 
 namespace {
+
+/* the ABI has no globals: a call leaves the caller's current device as it found it */
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 int fail(vs_ctx *c, int code, const char *fmt, ...)
 {
@@ -571,6 +578,7 @@ bool rows_overlap(std::vector<std::pair<uint64_t, uint64_t>> &r)
 int run_batch(vs_ctx *ctx, const Batch &b)
 {
     if (!ctx) return VS_EINVAL;
+    DeviceGuard restore_device;
     HostProf prof(ctx->env_profile_host);
     if (b.n == 0) return VS_OK;
     if (!b.pcm_out) return fail(ctx, VS_EINVAL, "pcm_out is NULL");
@@ -691,6 +699,18 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         return fail(ctx, VS_EINVAL, "pcm/raw/flow buffers must be all host or all device");
     if (out_dev && ctx->slots.size() != 1) return fail(ctx, VS_EINVAL, "device buffers need a single-device ctx");
     if (out_dev && odev != ctx->slots[0].dev) return fail(ctx, VS_EINVAL, "device buffer lives on device %d, ctx on %d", odev, ctx->slots[0].dev);
+    if (out_dev && b.mode == VS_MODE_FILTER) {
+        /* time-chunks of a row read flow samples that belong to the previous chunk's output range (carry warm-up):
+         * the filter cannot run in place on device memory (host buffers are staged apart) */
+        uint64_t ilo = ~0ull, ihi = 0, olo = ~0ull, ohi = 0;
+        for (size_t i = 0; i < n; i++) {
+            ilo = std::min(ilo, hs[i].in_off); ihi = std::max(ihi, hs[i].in_off + hs[i].n);
+            olo = std::min(olo, hs[i].out_off); ohi = std::max(ohi, hs[i].out_off + hs[i].n);
+        }
+        const uintptr_t i0 = reinterpret_cast<uintptr_t>(b.flow_in + ilo), i1 = reinterpret_cast<uintptr_t>(b.flow_in + ihi);
+        const uintptr_t o0 = reinterpret_cast<uintptr_t>(b.pcm_out + olo), o1 = reinterpret_cast<uintptr_t>(b.pcm_out + ohi);
+        if (i0 < o1 && o0 < i1) return fail(ctx, VS_EOVERLAP, "flow_in and pcm_out overlap in device memory");
+    }
 
     /* ---- 3. contiguous stream ranges per device slot, balanced by samples ------ */
     const size_t nslots = ctx->slots.size();
@@ -1045,7 +1065,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 else {
                     const bool busy = cudaEventQuery(sl.call_done[(cp + VS_DEPTH - 1u) % VS_DEPTH]) == cudaErrorNotReady;
                     (void)cudaGetLastError();
-                    plan_warps = pa.n_streams <= (any_noise ? VS_PLAN_WARP_MAX_NOISE : busy ? VS_PLAN_WARP_MAX : VS_PLAN_WARP_MAX_IDLE);
+                    plan_warps = pa.n_streams <= (busy ? VS_PLAN_WARP_MAX : any_noise ? VS_PLAN_WARP_MAX_NOISE : VS_PLAN_WARP_MAX_IDLE);
                 }
                 CU(vs_launch_plan(pa, want_log, plan_warps, pstream));
                 ctx->timing.launches++;
@@ -1217,6 +1237,7 @@ int vs_ctx_create(vs_ctx **out, const int *devices, int n_devices, uint32_t flag
     (void)flags;
     if (!out) return VS_EINVAL;
     *out = nullptr;
+    DeviceGuard restore_device;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { cudaGetLastError(); return VS_ENODEV; }
     std::vector<int> devs;
@@ -1227,9 +1248,6 @@ int vs_ctx_create(vs_ctx **out, const int *devices, int n_devices, uint32_t flag
     ctx->env_profile_host = getenv("VS_PROFILE_HOST") != nullptr;     /* debugging aids, read once */
     ctx->env_sync_plan = getenv("VS_DEBUG_SYNCPLAN") != nullptr;
     compute_warmups(ctx);
-    std::vector<double> coef(VS_NUM_PRESETS * VS_RING, 0.0);
-    for (int k = 0; k < VS_NUM_PRESETS; k++)
-        for (int j = 0; j <= VS_ORDER; j++) coef[k * VS_RING + j] = vs_preset_den[k][j];
     for (int d : devs) {
         if (d < 0 || d >= count) { vs_ctx_destroy(ctx); return VS_ENODEV; }
         cudaDeviceProp prop;
@@ -1252,9 +1270,7 @@ int vs_ctx_create(vs_ctx **out, const int *devices, int n_devices, uint32_t flag
                   cudaEventCreateWithFlags(&s.slab_done[1], cudaEventDisableTiming) == cudaSuccess &&
                   cudaEventCreateWithFlags(&s.slab_ready, cudaEventDisableTiming) == cudaSuccess &&
                   vs_render_init_device() == cudaSuccess &&
-                  cudaMalloc(&s.coef.p, coef.size() * sizeof(double)) == cudaSuccess &&
-                  cudaMemcpy(s.coef.p, coef.data(), coef.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
-        s.coef.cap = coef.size() * sizeof(double);
+                  true;
         for (int k = 0; ok && k < VS_DEPTH; k++)
             ok = cudaEventCreateWithFlags(&s.call_done[k], cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&s.plan_done[k], cudaEventDisableTiming) == cudaSuccess;
@@ -1268,12 +1284,13 @@ int vs_ctx_create(vs_ctx **out, const int *devices, int n_devices, uint32_t flag
 void vs_ctx_destroy(vs_ctx *ctx)
 {
     if (!ctx) return;
+    DeviceGuard restore_device;
     for (Slot &s : ctx->slots) {
         cudaSetDevice(s.dev);
         if (s.compute) cudaStreamSynchronize(s.compute);
         if (s.copy) cudaStreamSynchronize(s.copy);
         for (int k = 0; k < 2; k++) if (s.plans[k]) cudaStreamSynchronize(s.plans[k]);
-        std::vector<DevBuf *> bufs = {&s.costab, &s.coef, &s.pcm[0], &s.pcm[1], &s.raw[0], &s.raw[1], &s.flowin[0], &s.flowin[1], &s.log};
+        std::vector<DevBuf *> bufs = {&s.costab, &s.pcm[0], &s.pcm[1], &s.raw[0], &s.raw[1], &s.flowin[0], &s.flowin[1], &s.log};
         std::vector<PinBuf *> pins;
         for (int k = 0; k < VS_DEPTH; k++) {
             for (DevBuf *b : {&s.streams[k], &s.chunks[k], &s.order[k], &s.table[k], &s.snap[k], &s.nper[k], &s.status[k]}) bufs.push_back(b);
@@ -1320,6 +1337,7 @@ int vs_ctx_set_stream(vs_ctx *ctx, int slot, void *cuda_stream)
 {
     if (!ctx || slot < 0 || (size_t)slot >= ctx->slots.size()) return VS_EINVAL;
     Slot &s = ctx->slots[slot];
+    DeviceGuard restore_device;
     CU(cudaSetDevice(s.dev));
     CU(cudaStreamSynchronize(s.compute));
     if (s.own_compute) CU(cudaStreamDestroy(s.compute));
@@ -1331,6 +1349,7 @@ int vs_ctx_set_stream(vs_ctx *ctx, int slot, void *cuda_stream)
 int vs_sync(vs_ctx *ctx)
 {
     if (!ctx) return VS_EINVAL;
+    DeviceGuard restore_device;
     int status = 0;
     for (Slot &s : ctx->slots) {
         CU(cudaSetDevice(s.dev));
@@ -1377,6 +1396,7 @@ void vs_host_free(void *p) { if (p) cudaFreeHost(p); }
 int vs_measure_fp64_peak(vs_ctx *ctx, double *tflops_out, double *sm_mhz_out)
 {
     if (!ctx || !tflops_out) return VS_EINVAL;
+    DeviceGuard restore_device;
     Slot &s = ctx->slots[0];
     CU(cudaSetDevice(s.dev));
     const int blocks = s.sm_count * 8, iters = 1 << 16;
@@ -1458,7 +1478,8 @@ int vs_vowel_noise_batch(vs_ctx *ctx, int16_t *pcm, const uint64_t *offsets, con
     if (n > 0x7fffffffull) return fail(ctx, VS_EINVAL, "too many streams");
     int rc = vs_sync(ctx);                                    /* in-place: earlier work on this PCM must have landed */
     if (rc) return rc;
-    Slot &sl = ctx->slots[0];
+    DeviceGuard restore_device;
+    Slot &sl = ctx->slots[0];                                 /* one warp per stream and 0.75 ms for 4096 x 1 s: one device is plenty */
     CU(cudaSetDevice(sl.dev));
     std::vector<VsNoiseRow> rows(n);
     uint64_t max_n = 0, lo = ~0ull, hi = 0;
@@ -1490,10 +1511,18 @@ int vs_vowel_noise_batch(vs_ctx *ctx, int16_t *pcm, const uint64_t *offsets, con
         CU(cudaMemcpyAsync(sl.pcm[0].p, pcm + lo, (hi - lo) * sizeof(int16_t), cudaMemcpyHostToDevice, sl.compute));
     }
     CU(vs_launch_vnoise(d_pcm, (const VsNoiseRow *)sl.log.p, (uint32_t)n, sl.compute));
-    if (!on_dev)
-        for (size_t i = 0; i < n; i++)                         /* only the rows: gaps between them are not ours */
-            if (rows[i].n && rows[i].snr > 0.0f)
-                CU(cudaMemcpyAsync(pcm + rows[i].off, d_pcm + rows[i].off, rows[i].n * sizeof(int16_t), cudaMemcpyDeviceToHost, sl.compute));
+    if (!on_dev) {
+        /* only the rows come back (gaps between them are not ours); rows that touch travel as one copy */
+        uint64_t run_lo = 0, run_hi = 0;
+        for (size_t i = 0; i <= n; i++) {
+            const bool take = i < n && rows[i].n && rows[i].snr > 0.0f;
+            if (take && run_hi > run_lo && rows[i].off == run_hi) { run_hi += rows[i].n; continue; }
+            if (run_hi > run_lo)
+                CU(cudaMemcpyAsync(pcm + run_lo, d_pcm + run_lo, (run_hi - run_lo) * sizeof(int16_t), cudaMemcpyDeviceToHost, sl.compute));
+            run_lo = take ? rows[i].off : 0;
+            run_hi = take ? rows[i].off + rows[i].n : 0;
+        }
+    }
     CU(cudaStreamSynchronize(sl.compute));                    /* `rows` is pageable host memory */
     return VS_OK;
 }

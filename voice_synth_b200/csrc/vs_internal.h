@@ -13,7 +13,7 @@
                                   the VS_PLAN_SMS SMs the chunk planner keeps free, instead of being starved of
                                   issue slots by the render warps of call k (measured: 0.35 -> 0.7 ms)        */
 #define VS_PLAN_SMEM (96 * 1024)
-#define VS_PLAN_SMS  16         /* most SMs the chunk planner leaves to the plan kernels of the next two calls */
+#define VS_PLAN_SMS  32         /* most SMs the chunk planner leaves to the plan kernels of the next two calls */
 /* batches up to this many streams get one WARP per stream in the plan kernel (vs_api.cu, plan launch) */
 #define VS_PLAN_WARP_MAX       1024    /* while the previous call is still on the GPU */
 #define VS_PLAN_WARP_MAX_IDLE  6144    /* GPU idle: the plan kernel is the call's critical path */
