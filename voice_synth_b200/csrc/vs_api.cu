@@ -493,7 +493,7 @@ void plan_filter_chunks(vs_ctx *ctx, const Slot &slot, const std::vector<VsStrea
     /* rows per wave; a few SMs stay free for the plan kernels of the next two calls (one CTA of VS_PLAN_NT streams per
      * SM each, see VS_PLAN_SMEM) */
     const int plan_ctas = (int)((ns + VS_PLAN_NT - 1) / VS_PLAN_NT);
-    const int reserve = std::min(VS_PLAN_SMS, 2 * plan_ctas);
+    const int reserve = 2 * plan_ctas <= VS_PLAN_SMS ? 2 * plan_ctas : 0;       /* large batches: the plan needs every SM anyway */
     const int render_sms = slot.sm_count > 4 * VS_PLAN_SMS ? slot.sm_count - reserve : slot.sm_count;
     const double cap = (double)render_sms * VS_NT;
     /* streams of equal (length, preset) get equal chunk counts: plan over the distinct classes */
@@ -874,12 +874,12 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 size_t i1 = i0;
                 const int pr = preset_of(ids[i0]);
                 while (i1 < ids.size() && preset_of(ids[i1]) == pr) i1++;
-                for (; pr_done < pr; pr_done++) gm.cta_end[pr_done] = (uint32_t)((order.size() - r_first) / VS_NT);
+                for (; pr_done < pr; pr_done++) gm.cta_end[pr_done] = (uint32_t)((order.size() - r_first) / 32);
                 for (size_t i = i0; i < i1; i++) order.push_back(ids[i]);
-                while ((order.size() - r_first) % VS_NT) order.push_back(VS_NO_CHUNK);
+                while ((order.size() - r_first) % 32) order.push_back(VS_NO_CHUNK);
                 i0 = i1;
             }
-            for (; pr_done < VS_NUM_PRESETS; pr_done++) gm.cta_end[pr_done] = (uint32_t)((order.size() - r_first) / VS_NT);
+            for (; pr_done < VS_NUM_PRESETS; pr_done++) gm.cta_end[pr_done] = (uint32_t)((order.size() - r_first) / 32);
             /* pulse-table cache: the largest sum of distinct (padded) tables over the warps of the slab */
             gm.cache_doubles = 0;
             if (b.mode != VS_MODE_FILTER) {
@@ -1132,13 +1132,23 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                  * (a warp that needs more renders its rows with the general generator) */
                 const uint32_t budget = (b.mode == VS_MODE_FLOW ? 100u : 200u) * 1024u / 4u;
                 const uint32_t fixed = tile_bytes + R * 32u * VS_TAB_ENTRY_BYTES(compact);
-                uint32_t cache = (sl.plan_geom[k].cache_doubles + 1u) & ~1u;
+                uint32_t cache = std::max(16u, (sl.plan_geom[k].cache_doubles + 1u) & ~1u);
                 if (fixed + 4096u <= budget) cache = std::min(cache, ((budget - fixed) / 8u) & ~1u);
                 const uint32_t wbytes = fixed + cache * 8u;
                 if (R <= 64 && wbytes <= budget) {
                     gen = VS_GEN_FAST;
                     ra.warp_bytes = wbytes; ra.ring_R = R; ra.ring_fetch = per_win + 2u; ra.ring_ahead = ahead; ra.cache_doubles = cache;
                 }
+            }
+            {   /* persistent grid: one CTA per render SM (the plan kernels of the next calls own the others); the
+                 * flow-only kernel is small, a few of its CTAs share an SM */
+                const uint32_t blocks = (ra.n_rows / 32u + 3u) / 4u;
+                const int plan_ctas = (int)((ns + VS_PLAN_NT - 1) / VS_PLAN_NT);
+                const int reserve = 2 * plan_ctas <= VS_PLAN_SMS ? 2 * plan_ctas : 0;       /* large batches: the plan needs every SM anyway */
+                const uint32_t sms = (uint32_t)std::max(1, sl.sm_count - reserve);
+                uint32_t per_sm = 1;
+                if (b.mode == VS_MODE_FLOW) per_sm = std::max(1u, std::min(4u, (220u * 1024u) / (4u * ra.warp_bytes + (any_noise ? 16u * 1024u : 0u) + 1024u)));
+                ra.grid = std::min(blocks, sms * per_sm);
             }
             const int filt = exact ? VS_FILT_EXACT : ((int_filter && !b.raw_out) ? VS_FILT_INT : VS_FILT_FMA);
             CU(vs_launch_render(ra, b.mode, gen, any_noise, filt, sl.compute));

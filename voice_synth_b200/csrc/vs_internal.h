@@ -113,10 +113,10 @@ struct VsRenderArgs {
     const VsStream *streams;
     const VsChunk  *chunks;
     const uint32_t *order;          /* render row t works on chunk order[t]; VS_NO_CHUNK = padding   */
-    uint32_t        cta_end[VS_NUM_PRESETS_I];   /* CTAs [cta_end[p-1], cta_end[p]) serve vowel preset p: the preset is a
-                                       function of blockIdx and kernel parameters only, so the coefficients are
-                                       read into UNIFORM registers (DFMA R, R, UR, R)                 */
-    uint32_t        n_rows;         /* rows incl. padding, multiple of VS_NT                         */
+    uint32_t        cta_end[VS_NUM_PRESETS_I];   /* blocks of 32 rows [cta_end[p-1], cta_end[p]) belong to vowel preset p      */
+    uint32_t        n_rows;         /* rows incl. padding, multiple of 32                            */
+    uint32_t        grid;           /* CTAs to launch: one per render SM (flow only: a few per SM); they take the blocks
+                                       of 32 rows round robin                                        */
     const void     *table;          /* VsPeriod[], VsPeriodC[] or VsPeriodN[]                        */
     int             compact;        /* VS_TAB_*                                                      */
     const uint32_t *n_periods;      /* [n_streams] periods the plan kernel wrote                     */

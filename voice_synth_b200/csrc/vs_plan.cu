@@ -19,6 +19,37 @@
 /* ================================================================================================
  * PLAN: one thread per stream
  * ============================================================================================== */
+/* step over n random() values (the period's noise draws are the render kernel's business).  Three at a time: value k
+ * needs r[k-31] from the state array and r[k-3], which for the next three values are the three just made -- they stay
+ * in registers, so consecutive trios depend on each other through one integer add only, the loads of the old
+ * values run ahead and the stores trail behind. */
+template <int STRIDE>
+__device__ __forceinline__ void vs_rng_skip(VsRng &g, uint32_t n)
+{
+    if (n >= 3) {
+        int f = g.f;
+        int b = f >= 3 ? f - 3 : f + 28;
+        uint32_t p0 = g.r[b * STRIDE];
+        b = b == VS_RNG_DEG - 1 ? 0 : b + 1;
+        uint32_t p1 = g.r[b * STRIDE];
+        b = b == VS_RNG_DEG - 1 ? 0 : b + 1;
+        uint32_t p2 = g.r[b * STRIDE];
+        do {
+            const int f0 = f, f1 = f0 == VS_RNG_DEG - 1 ? 0 : f0 + 1, f2 = f1 == VS_RNG_DEG - 1 ? 0 : f1 + 1;
+            p0 += g.r[f0 * STRIDE];
+            p1 += g.r[f1 * STRIDE];
+            p2 += g.r[f2 * STRIDE];
+            g.r[f0 * STRIDE] = p0;
+            g.r[f1 * STRIDE] = p1;
+            g.r[f2 * STRIDE] = p2;
+            f = f2 == VS_RNG_DEG - 1 ? 0 : f2 + 1;
+            n -= 3;
+        } while (n >= 3);
+        g.f = f;
+    }
+    for (; n > 0; n--) (void)vs_rng_next<STRIDE>(g);
+}
+
 /* one period into the table, in the format the render kernel asked for */
 __device__ __forceinline__ void vs_store_period(void *table, int fmt, uint64_t idx, float A, float Knew, uint32_t start, int T,
                                                 uint32_t nd, int T3, int T4, int ndw)
@@ -139,6 +170,7 @@ __global__ void __launch_bounds__(VS_PLAN_NT, 1) vs_plan_kernel(const VsPlanArgs
             float aux_new = 0.0f, aux_old = 0.0f;
             bool moved = false;
             const int T4_old = T4;
+#pragma unroll 4
             for (int i = 0; i < T2; i++) {
                 int x = vs_rising(Ad, __ldg(ht + i));
                 if (x < DCi) { x = DCs; T4 = i; moved = true; aux_new = 0.0f; }
@@ -148,6 +180,7 @@ __global__ void __launch_bounds__(VS_PLAN_NT, 1) vs_plan_kernel(const VsPlanArgs
             }
             float aux = moved ? aux_new : aux_old;
             int i;
+#pragma unroll 4
             for (i = T2; i < 2 * T2; i++) {
                 const int x = vs_falling(Ad, Kd, __ldg(ct + i - T2));
                 if (x < DCi) break;
@@ -168,7 +201,7 @@ __global__ void __launch_bounds__(VS_PLAN_NT, 1) vs_plan_kernel(const VsPlanArgs
                     }
                     w_pow = __fdiv_rn(wa, (float)T);
                 } else {
-                    for (uint32_t k = 0; k < n_noise; k++) (void)vs_rng_next<VS_PLAN_NT>(g);
+                    vs_rng_skip<VS_PLAN_NT>(g, n_noise);
                 }
             }
         }

@@ -173,13 +173,6 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
     const int pair = warp & 3;
     const bool is_f = HASFILT && warp >= 4;                 /* the higher warp id wins the issue slot when both are ready */
 
-    /* vowel preset of this CTA: a function of blockIdx and kernel parameters */
-    int preset = 0;
-    if (HASFILT) {
-#pragma unroll
-        for (int p = 0; p < VS_NUM_PRESETS - 1; p++) preset += blockIdx.x >= a.cta_end[p] ? 1 : 0;
-    }
-
     /* shared memory: per pair [NT tiles | period ring | pulse-table cache | row descriptors], then the CTA's RNG states */
     const uint32_t tile_off = (uint32_t)pair * a.warp_bytes;
     const uint32_t ring_off = tile_off + (uint32_t)NT * TILE;
@@ -187,8 +180,21 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
     uint32_t *s_rng = reinterpret_cast<uint32_t *>(smem + 4u * a.warp_bytes);      /* [31][VS_NT], NOISE only */
 
+    /* PERSISTENT: the grid has one CTA per render SM (the host keeps the other SMs free for the plan kernels of the
+     * next calls); a pair of warps takes blocks of 32 rows round robin until the batch is done.  Rows are sorted
+     * longest first inside a preset, so every pair gets a similar mix. */
+    const uint32_t n_blocks = a.n_rows / 32u;
+    for (uint32_t pb = blockIdx.x * 4u + (uint32_t)pair; pb < n_blocks; pb += gridDim.x * 4u) {
+    /* vowel preset of this block of rows: a function of its index and kernel parameters (rows are grouped by preset
+     * and padded to whole blocks) */
+    int preset = 0;
+    if (HASFILT) {
+#pragma unroll
+        for (int p = 0; p < VS_NUM_PRESETS - 1; p++) preset += pb >= a.cta_end[p] ? 1 : 0;
+    }
+
     /* ---- the lane's row (lane l of F and lane l of G serve the same row) -------------------------------- */
-    const uint32_t t = blockIdx.x * VS_NT + (uint32_t)pair * 32u + (uint32_t)lane;
+    const uint32_t t = pb * 32u + (uint32_t)lane;
     const uint32_t chunk_id = t < a.n_rows ? __ldg(a.order + t) : VS_NO_CHUNK;
     bool active = chunk_id != VS_NO_CHUNK;
     int lo = 0, hi = 0, nstart = 0;
@@ -233,7 +239,7 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
             default: vs_filter_rows<WIN, NT, FILT, RAW, 9>(tiles, pair, nwin, gaind, pred, rrow, blk0, lo, hi); break;
 #undef VS_F_CASE
         }
-        return;
+        continue;
     }
 
     /* =====================================================================================================
@@ -287,6 +293,7 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
      * first or last chunks of many voices -- falls back to the general generator for its 32 rows. */
     bool wfast = FAST;
     if (FAST) {
+        vs_cp_async_wait_all();                             /* ring entries still in flight from the previous block of rows */
         /* pulse tables into the pair's cache: one copy per distinct table of the warp's rows */
         const uint32_t key = active ? pulse_off : 0xffffffffu;
         const uint32_t grp = __match_any_sync(VS_FULL, key);
@@ -304,6 +311,10 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
         const uint32_t base = incl - mine;
         const uint32_t lbase = __shfl_sync(VS_FULL, base, leader);
         wfast = __shfl_sync(VS_FULL, incl, 31) <= a.cache_doubles;
+#ifdef VS_DEBUG_BOUNDS
+        if (active && 2u * (uint32_t)T2 > (uint32_t)tpad) atomicExch(a.status, -110);
+        if (cache_off + a.cache_doubles * 8u > 4u * a.warp_bytes) atomicExch(a.status, -111);
+#endif
         uint32_t leaders = wfast ? __ballot_sync(VS_FULL, mine > 0u) : 0u;
         double *cache = reinterpret_cast<double *>(smem + cache_off);
         while (leaders) {
@@ -313,7 +324,7 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
             const uint32_t np = __shfl_sync(VS_FULL, mine, L);
             for (uint32_t k = lane; k < np; k += 32) cache[dst + k] = k < n ? __ldg(a.costab + src + k) : 0.0;
         }
-        tb = cache_off + lbase * 8u;
+        tb = active ? cache_off + lbase * 8u : cache_off;  /* rows of padding read (and discard) the cache's first entries */
         /* first entries of the period ring, then the first period as `next` of an empty current period that
          * covers the slots before the row's first sample */
         if (active && wfast) {
@@ -394,6 +405,9 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
         const bool pr = icT + VS_GROUP >= 0;
         ic += VS_GROUP;
         if (pr) { ic -= Tc; Adc = Adn; Tc = Tn; q++; }
+#ifdef VS_DEBUG_BOUNDS
+        if (active && (Tc < VS_GROUP || Tc > tpad || ic < 0 || ic >= Tc)) { atomicExch(a.status, -100 - (Tc > tpad ? 1 : Tc < VS_GROUP ? 2 : 3)); Tc = tpad; ic = 0; }
+#endif
         const bool valid = q < qlast;
         if (NOISE) {
             /* the promoted period's jitter / shimmer / K draws come before its noise draws (:283,:298,:325); none of
@@ -533,6 +547,9 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
     auto store_window = [&](const int w, const int ti) {
         const int wb = blk0 + w * WIN;
         const int a0 = max(wb, lo), b0 = min(wb + WIN, hi);
+#ifdef VS_DEBUG_BOUNDS
+        if (b0 > a0 && (orow == nullptr || a0 < 0 || b0 - wb > WIN || a0 < wb)) { atomicExch(a.status, -120); return; }
+#endif
         if (b0 > a0) {
             const uint32_t trow = tile_off + (uint32_t)ti * TILE + (uint32_t)lane * TSB;
             const int a8 = wb + ((a0 - wb + 7) & ~7), b8 = wb + ((b0 - wb) & ~7);
@@ -572,6 +589,7 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
         }
     }
     vs_bulk_wait_read<0>();                                 /* shared memory must outlive the copies that read it */
+    }   /* next block of 32 rows */
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -591,7 +609,7 @@ int vs_render_tiles(int mode) { return VS_RENDER_TILES(mode); }
 template <int MODE, int GEN, bool NOISE, int FILT, bool RAW>
 static cudaError_t vs_go(const VsRenderArgs &a, cudaStream_t s)
 {
-    const unsigned grid = a.n_rows / VS_NT;
+    const unsigned grid = a.grid;
     const int dyn = 4 * (int)a.warp_bytes + (NOISE ? VS_RNG_DEG * VS_NT * 4 : 0);      /* warp_bytes: per pair of warps */
     /* the attribute is per device and per kernel: set it whenever a launch needs more than the last one did */
     static int granted[16] = {0};
