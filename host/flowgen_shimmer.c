@@ -43,7 +43,10 @@ int main(int argc, char **argv)
     const uint32_t data_bytes = (uint32_t)(long)(a.dur * (float)a.fs * 2);
     if (vs_wav_write_header(out, (uint32_t)a.fs, data_bytes)) { printf("Error while writing header to %s\n", a.out_path); return 1; }
 
-    printf("Synthetic glottal flow generator (Fant 1979 model) -- libvoicesynth_cuda\nOutput file = %s\n", a.out_path);
+    /* the reference's banner, line for line (flowgen_shimmer.c:576-588; no newline after its second sentence) */
+    printf("(c) Maurilio N. Vieira, 1996\nSynthetic vowel generator\n");
+    printf("ported to gcc - Joao SANSAO, Feb. 2007");
+    printf("Output file = %s\n", a.out_path);
     if (a.flags & VS_F_NOISE) printf("SNR: %5.2f dB, ", 10.0 * log10((double)a.noise));
     printf("Fs=%ld Hz, Dur=%5.2f s, Fg=%d Hz, Amp = %d, DCflow=%5.2f\n", (long)a.fs, a.dur, (int)a.Fg, a.amp, a.DC);
     printf("Wait...");

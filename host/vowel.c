@@ -32,7 +32,11 @@ int main(int argc, char **argv)
     if (!out) { printf("Error while creating file (%s)\n", a.out_path); return 1; }
     vs_wav_write_header(out, wi.sample_rate, wi.data_bytes);          /* the reference copies the input header */
 
-    printf("Vocal-tract filter, vowel /%c/ -- libvoicesynth_cuda\n", a.preset);
+    /* the reference's banner (vowel_new.c:404-410) */
+    printf(" \nMaurilio N. Vieira, 28 mar 97. \n");
+    printf(" Cascade Formant Synthesiser\n");
+    printf(" Formant frequencies/bandwithds from Rabiner & Schafer (1978),\n");
+    printf(" Digital Processing of Speech Signals, Prentice Hall, pp. 74-77\n");
     printf("pre_emphasis=%5.2f, gain=%5.2f, snr=%5.2f\nWait...", a.pre, a.gain, a.snr_linear);
 
     int dev = getenv("VS_DEVICE") ? atoi(getenv("VS_DEVICE")) : 0;
@@ -43,6 +47,10 @@ int main(int argc, char **argv)
     const uint8_t preset = (uint8_t)a.preset;
     const uint64_t ns = n;
     vs_filter_params f = {&preset, &a.gain, &a.pre};
+    /* -n: the output noise of a frame is scaled by the frame's power after quantisation (vowel_new.c:302-324), so a
+     * sample that differs by one LSB would change every noise value of its frame: filter in the reference's own
+     * operation order there (bit-exact); without -n the fast filter (+-1 LSB) is used */
+    if (a.has_noise) vs_ctx_set_option(ctx, VS_OPT_EXACT_FILTER, 1.0);
     if (n) {
         rc = vs_vowel_filter_batch(ctx, flow, NULL, &ns, &f, 1, pcm, NULL, NULL);
         if (rc) { fprintf(stderr, "vowel: %s (%s)\n", vs_strerror(rc), vs_last_error(ctx)); return 1; }

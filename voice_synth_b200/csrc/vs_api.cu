@@ -1124,8 +1124,10 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             int gen = VS_GEN_SIMPLE;
             ra.warp_bytes = tile_bytes;
             if (b.mode != VS_MODE_FILTER && compact != VS_TAB_FULL && amp_fits && !ctx->opt_simple_gen && t_min >= 24 && t_max <= 8192) {
-                const uint32_t per_win = (uint32_t)(win / t_min) + 2u;      /* pitch periods a lane can start in one window */
-                const uint32_t ahead = 2u * per_win + 3u;
+                /* pitch periods a lane can enter in one window (+1: the generator may already have promoted the period
+                 * that starts with the next window); the ring holds two windows' worth */
+                const uint32_t per_win = (uint32_t)((win + t_min - 1) / t_min) + 1u;
+                const uint32_t ahead = 2u * per_win + 2u;
                 uint32_t R = 8;
                 while (R < ahead) R <<= 1;
                 /* the pulse-table cache: what the typical warp of this row order needs, as far as shared memory goes

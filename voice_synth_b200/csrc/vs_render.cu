@@ -85,8 +85,8 @@ __device__ __forceinline__ void vs_filter_rows(unsigned char *tiles /* the lane'
     double y[VS_RING];
 #pragma unroll
     for (int j = 0; j < VS_RING; j++) y[j] = 0.0;
-    const int gain_i = (int)gaind, pre_i = (int)pred;
-    int xg_prev = 0, mbase = blk0, ti = 0;
+    const int gain_i = (int)gaind, npre_i = -(int)pred;
+    int x_prev = 0, mbase = blk0, ti = 0;
 
     vs_pair_barrier(pair);                                  /* window 0 generated */
     for (int w = 0; w < nwin; w++) {
@@ -109,9 +109,8 @@ __device__ __forceinline__ void vs_filter_rows(unsigned char *tiles /* the lane'
                     if (FILT == VS_FILT_INT) {
                         /* gain and pre-emphasis on the integer input; the recurrence then yields the
                          * pre-emphasised waveform directly (the filter is LTI) */
-                        const int xg = xi * gain_i;
-                        acc = (double)(xg - xg_prev * pre_i);
-                        xg_prev = xg;
+                        acc = (double)((xi + x_prev * npre_i) * gain_i);
+                        x_prev = xi;
 #pragma unroll
                         for (int j = VS_ORDER; j >= 1; j--) acc = __fma_rn(y[(k + VS_RING - j) % VS_RING], c_ncoef[PRESET][j], acc);
                         v = acc;
