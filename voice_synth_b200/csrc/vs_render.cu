@@ -61,6 +61,25 @@ __device__ __forceinline__ void vs_bulk_commit() { asm volatile("cp.async.bulk.c
 template <int N>
 __device__ __forceinline__ void vs_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
+/* shared-memory accesses by 32-bit shared-window address: no generic-to-shared conversion in the sample loop, the
+ * constant part of the address folds into the instruction */
+__device__ __forceinline__ double vs_lds_f64(uint32_t addr)
+{
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t vs_lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void vs_sts_u32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 /* the glottal-noise sample (flowgen_shimmer.c:387,394) in two FP64 operations: t = r/M - 1/2, w = ceil(t*NDW).
  * Equal to the reference's divide / multiply / subtract / ceil for every r and NDW < 2^19 (proof and exhaustive
  * check around every breakpoint: tests/tools/noisecheck.c). */
@@ -362,7 +381,8 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
     auto gen_fast = [&](int (&x)[VS_GROUP], const bool first) {
         const int icT = ic - Tc;
         const double Adn = (double)An;
-        const unsigned char *bc = smem + tb + (uint32_t)ic * 8u, *bn = smem + tb + icT * 8;   /* table entry of sample 0 in the current / next period */
+        uint32_t bc = smem_base + tb + (uint32_t)ic * 8u, bn = smem_base + tb + (uint32_t)(icT * 8);   /* table entry of sample 0 in the current / next period */
+        asm("" : "+r"(bc), "+r"(bn));                       /* keep them as two addresses: one select per sample, not select + scale + add */
         /* glottal noise (flowgen_shimmer.c:385-399 with T4 == 0): the samples from the closure instant T3 to the
          * period's end each take one random() value.  Bit u of nm: sample u is one of them. */
         uint32_t nm = 0;
@@ -373,11 +393,11 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
             nm = nz ? ((~low(T3c - ic) & lk) | (~low(T3n - icT) & ~lk)) & 0xffu : 0u;
             ndwn_d = (double)ndwn;
         }
-        unsigned char *rcol = reinterpret_cast<unsigned char *>(rng.r);
+        const uint32_t rcol = (uint32_t)__cvta_generic_to_shared(rng.r);
 #pragma unroll
         for (int u = 0; u < VS_GROUP; u++) {
             const bool nx = icT + u >= 0;                   /* the sample belongs to the next period */
-            const double fac = *reinterpret_cast<const double *>((nx ? bn : bc) + u * 8);
+            const double fac = vs_lds_f64((nx ? bn : bc) + (uint32_t)(u * 8));
             const double A = nx ? Adn : Adc;
             const int v = __double2int_ru(__dmul_rn(A, fac));
             int xv = max(v, first ? (nx ? DCs : 0) : DCs);
@@ -389,9 +409,9 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
                 const bool ns = ((nm >> u) & 1u) != 0u;
                 const bool dr = ns || skip > 0;
                 skip = max(skip - 1, 0);
-                const uint32_t old = *reinterpret_cast<const uint32_t *>(rcol + rf);
+                const uint32_t old = vs_lds_u32(rcol + rf);
                 const uint32_t val = old + r3;
-                *reinterpret_cast<uint32_t *>(rcol + rf) = dr ? val : old;
+                vs_sts_u32(rcol + rf, dr ? val : old);
                 const uint32_t rfn = rf + VS_NT * 4u == VS_RNG_DEG * VS_NT * 4u ? 0u : rf + VS_NT * 4u;
                 rf = dr ? rfn : rf;
                 r3 = dr ? r2 : r3; r2 = dr ? r1 : r2; r1 = dr ? val : r1;
@@ -413,9 +433,9 @@ __global__ void __launch_bounds__(VS_RENDER_THREADS(MODE), MODE == VS_MODE_FLOW 
              * its noise samples lie in this group or in the first half of the next (T3 >= T2 >= 16) */
             if (pr) { T3c = T3n; ndwc = ndwn_d; skip = nz ? npn : 0; }
             while (__any_sync(VS_FULL, skip > 4)) {         /* rejection-heavy streams only: the next group's first samples take four */
-                const uint32_t val = *reinterpret_cast<const uint32_t *>(rcol + rf) + r3;
+                const uint32_t val = vs_lds_u32(rcol + rf) + r3;
                 if (skip > 4) {
-                    *reinterpret_cast<uint32_t *>(rcol + rf) = val;
+                    vs_sts_u32(rcol + rf, val);
                     rf = rf + VS_NT * 4u == VS_RNG_DEG * VS_NT * 4u ? 0u : rf + VS_NT * 4u;
                     r3 = r2; r2 = r1; r1 = val;
                     skip--;
