@@ -175,6 +175,30 @@ def ncu_traffic():
     return None
 
 
+def _cpus_of(spec):
+    cpus = set()
+    for part in spec.strip().split(","):
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def _topo_affinity(index):
+    """CPU affinity of GPU `index` as `nvidia-smi topo -m` reports it (used when sysfs has no NUMA node for the device)."""
+    out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+    header = None
+    for line in out.splitlines():
+        cols = [c for c in line.replace("\x1b[4m", "").replace("\x1b[0m", "").split("\t") if c.strip() != ""]
+        if header is None and "CPU Affinity" in line:
+            header = [c.strip() for c in cols]
+            continue
+        if header and cols and cols[0].strip() == f"GPU{index}":
+            pos = header.index("CPU Affinity") + 1          # the row has the GPU name in front
+            if pos < len(cols):
+                return cols[pos].strip()
+    return None
+
+
 def bind_near_gpu(index):
     """Run this rank on the CPUs of its GPU's NUMA node, so that the pinned host buffers it allocates are
     node-local (first touch) and the PCM does not cross the socket interconnect after crossing PCIe.
@@ -184,17 +208,19 @@ def bind_near_gpu(index):
         pr = torch.cuda.get_device_properties(index)
         bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
         node = int((pathlib.Path("/sys/bus/pci/devices") / bdf / "numa_node").read_text())
-        if node < 0:
-            return {"gpu": bdf, "node": node, "bound": False}
-        cpus = set()
-        for part in pathlib.Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
+        how = "sysfs"
+        if node >= 0:
+            cpus = _cpus_of(pathlib.Path(f"/sys/devices/system/node/node{node}/cpulist").read_text())
+        else:
+            spec = _topo_affinity(index)
+            if not spec:
+                return {"gpu": bdf, "node": node, "bound": False}
+            cpus, how = _cpus_of(spec), "nvidia-smi topo -m"
         use = cpus & os.sched_getaffinity(0)
         if not use:
-            return {"gpu": bdf, "node": node, "bound": False, "why": "no allowed CPU on that node"}
+            return {"gpu": bdf, "node": node, "bound": False, "why": "no allowed CPU near the GPU"}
         os.sched_setaffinity(0, use)
-        return {"gpu": bdf, "node": node, "bound": True, "cpus": len(use)}
+        return {"gpu": bdf, "node": node, "bound": True, "cpus": len(use), "from": how}
     except Exception as e:                                  # no sysfs, no such property: run unbound
         return {"bound": False, "why": type(e).__name__}
 

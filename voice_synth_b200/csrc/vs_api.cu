@@ -59,7 +59,8 @@ struct Slot {
     int sm_count = 148;
     cudaStream_t compute = nullptr;
     bool own_compute = true;
-    cudaStream_t copy = nullptr;
+    cudaStream_t copy = nullptr, copy2 = nullptr;    /* device->host: large runs go home in pieces alternating between the two */
+    cudaEvent_t copy2_done = nullptr;
     cudaStream_t plans[2] = {nullptr, nullptr};      /* descriptor upload + plan kernel; calls alternate between the two */
     cudaEvent_t call_done[VS_DEPTH] = {};            /* everything of the call that used ring slot p has finished (compute) */
     cudaEvent_t plan_done[VS_DEPTH] = {};
@@ -164,6 +165,7 @@ int dev_reserve(vs_ctx *ctx, Slot &s, DevBuf &b, size_t bytes)
         CU(cudaStreamSynchronize(s.plans[0]));
         CU(cudaStreamSynchronize(s.plans[1]));
         CU(cudaStreamSynchronize(s.compute));
+        CU(cudaStreamSynchronize(s.copy2));
         CU(cudaStreamSynchronize(s.copy));
         CU(cudaFree(b.p));
         b.p = nullptr; b.cap = 0;
@@ -1162,12 +1164,21 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 /* PCM home over PCIe on the copy stream while the next slab renders */
                 CU(cudaEventRecord(sl.slab_ready, sl.compute));
                 CU(cudaStreamWaitEvent(sl.copy, sl.slab_ready, 0));
-                /* merge rows that touch into runs: a dense batch is one copy per slab */
+                CU(cudaStreamWaitEvent(sl.copy2, sl.slab_ready, 0));
+                /* merge rows that touch into runs: a dense batch is one copy per slab -- cut into 16 MB pieces that
+                 * alternate between two copy streams, so that a second DMA engine keeps the link busy while the first
+                 * one finishes a piece */
                 uint64_t run_lo = hs[a0].out_off, run_hi = hs[a0].out_off + hs[a0].n;
                 auto flush = [&](uint64_t lo, uint64_t hi) -> cudaError_t {
                     ctx->timing.d2h_bytes += (hi - lo) * (sizeof(int16_t) + (b.raw_out ? sizeof(double) : 0));
-                    cudaError_t e = cudaMemcpyAsync(b.pcm_out + lo, d_pcm + (lo - geom[k].out_min), (hi - lo) * sizeof(int16_t),
-                                                    cudaMemcpyDeviceToHost, sl.copy);
+                    cudaError_t e = cudaSuccess;
+                    const uint64_t piece = 8u << 20;                               /* samples */
+                    unsigned which = 0;
+                    for (uint64_t p0 = lo; p0 < hi && e == cudaSuccess; p0 += piece, which ^= 1u) {
+                        const uint64_t p1 = std::min(hi, p0 + piece);
+                        e = cudaMemcpyAsync(b.pcm_out + p0, d_pcm + (p0 - geom[k].out_min), (p1 - p0) * sizeof(int16_t),
+                                            cudaMemcpyDeviceToHost, which ? sl.copy2 : sl.copy);
+                    }
                     if (e == cudaSuccess && b.raw_out)
                         e = cudaMemcpyAsync(b.raw_out + lo, d_raw + (lo - geom[k].out_min), (hi - lo) * sizeof(double),
                                             cudaMemcpyDeviceToHost, sl.copy);
@@ -1178,6 +1189,8 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                     else { CU(flush(run_lo, run_hi)); run_lo = hs[i].out_off; run_hi = run_lo + hs[i].n; }
                 }
                 CU(flush(run_lo, run_hi));
+                CU(cudaEventRecord(sl.copy2_done, sl.copy2));
+                CU(cudaStreamWaitEvent(sl.copy, sl.copy2_done, 0));
                 CU(cudaEventRecord(sl.slab_done[d], sl.copy));
                 sl.slab_done_valid[d] = true;
             }
@@ -1275,6 +1288,8 @@ int vs_ctx_create(vs_ctx **out, const int *devices, int n_devices, uint32_t flag
         bool ok = cudaSetDevice(d) == cudaSuccess &&
                   cudaStreamCreateWithFlags(&s.compute, cudaStreamNonBlocking) == cudaSuccess &&
                   cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&s.copy2, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&s.copy2_done, cudaEventDisableTiming) == cudaSuccess &&
                   cudaStreamCreateWithFlags(&s.plans[0], cudaStreamNonBlocking) == cudaSuccess &&
                   cudaStreamCreateWithFlags(&s.plans[1], cudaStreamNonBlocking) == cudaSuccess &&
 
@@ -1300,6 +1315,7 @@ void vs_ctx_destroy(vs_ctx *ctx)
     for (Slot &s : ctx->slots) {
         cudaSetDevice(s.dev);
         if (s.compute) cudaStreamSynchronize(s.compute);
+        if (s.copy2) cudaStreamSynchronize(s.copy2);
         if (s.copy) cudaStreamSynchronize(s.copy);
         for (int k = 0; k < 2; k++) if (s.plans[k]) cudaStreamSynchronize(s.plans[k]);
         std::vector<DevBuf *> bufs = {&s.costab, &s.pcm[0], &s.pcm[1], &s.raw[0], &s.raw[1], &s.flowin[0], &s.flowin[1], &s.log};
@@ -1319,6 +1335,8 @@ void vs_ctx_destroy(vs_ctx *ctx)
         if (s.slab_done[0]) cudaEventDestroy(s.slab_done[0]);
         if (s.slab_done[1]) cudaEventDestroy(s.slab_done[1]);
         if (s.slab_ready) cudaEventDestroy(s.slab_ready);
+        if (s.copy2_done) cudaEventDestroy(s.copy2_done);
+        if (s.copy2) cudaStreamDestroy(s.copy2);
         if (s.copy) cudaStreamDestroy(s.copy);
         if (s.compute && s.own_compute) cudaStreamDestroy(s.compute);
     }
@@ -1368,6 +1386,7 @@ int vs_sync(vs_ctx *ctx)
         CU(cudaStreamSynchronize(s.plans[0]));
         CU(cudaStreamSynchronize(s.plans[1]));
         CU(cudaStreamSynchronize(s.compute));
+        CU(cudaStreamSynchronize(s.copy2));
         CU(cudaStreamSynchronize(s.copy));
         for (int k = 0; k < VS_DEPTH; k++)
             if (s.h_status[k].p && *(int32_t *)s.h_status[k].p) { status = *(int32_t *)s.h_status[k].p; *(int32_t *)s.h_status[k].p = 0; }

@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(VS_PLANW_NT) vs_plan_warp_kernel(const VsPlanA
 {
     /* per random() value, in a ring of 64 slots (two rounds of 31 are outstanding at most):
      * 2+J, 2-J, 1/(2-J), 2P*J/(2-J); the same four for S; Knew */
-    __shared__ double s_itp[VS_PLANW_NT / 32][8][64];
+    __shared__ double s_itp[VS_PLANW_NT / 32][12][64];
     __shared__ float s_kn[VS_PLANW_NT / 32][64];
     __shared__ __align__(16) float s_sq[VS_PLANW_NT / 32][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -319,6 +319,10 @@ __global__ void __launch_bounds__(VS_PLANW_NT) vs_plan_warp_kernel(const VsPlanA
                 itp[1][slot] = den;
                 itp[2][slot] = y;
                 itp[3][slot] = q;
+                /* the same step as one FMA, dPer' ~ dPer*a + q (tight loop below), and the part of its error bound
+                 * that does not depend on dPer */
+                itp[8][slot] = __ddiv_rn(__dadd_rn(2.0, J), den);
+                itp[9][slot] = __dmul_rn(fabs(q), 1.7763568394002505e-15);
             }
             if (do_shm) {                                                  /* :297-301 */
                 const float eps = __fmul_rn((float)r, 4.656612873077393e-10f);
@@ -331,6 +335,8 @@ __global__ void __launch_bounds__(VS_PLANW_NT) vs_plan_warp_kernel(const VsPlanA
                 itp[5][slot] = den;
                 itp[6][slot] = y;
                 itp[7][slot] = q;
+                itp[10][slot] = __ddiv_rn(__dadd_rn(2.0, S), den);
+                itp[11][slot] = __dmul_rn(fabs(q), 1.7763568394002505e-15);
             }
             const double kq = __dsub_rn(vs_div_const((double)r, VS_RAND_MAX_D, VS_INV_RM), 0.5);   /* :325 */
             kn[slot] = __double2float_rn(__dmul_rn(Kbase, __dadd_rn(1.0, __dmul_rn(kv2, kq))));
@@ -387,13 +393,18 @@ __global__ void __launch_bounds__(VS_PLANW_NT) vs_plan_warp_kernel(const VsPlanA
             const int lim = base + (have_b ? 2 * VS_RNG_DEG : VS_RNG_DEG);
             while (pos + 3 <= lim && count < st.n && np < st.tab_cap) {
                 const int pj = pos & 63, ps = (pos + 1) & 63, pk = (pos + 2) & 63;
-                const double numj = __dmul_rn((double)dper, itp[0][pj]);
-                const double nums = __dmul_rn((double)dsh, itp[4][ps]);
-                bool dj, ds;
-                const double qj = vs_div_checked_y(numj, itp[1][pj], itp[2][pj], dj);
-                const double qs = vs_div_checked_y(nums, itp[5][ps], itp[6][ps], ds);
-                const float curJ = __double2float_rn(__dadd_rn(qj, itp[3][pj]));
-                const float curS = __double2float_rn(__dadd_rn(qs, itp[7][ps]));
+                /* The reference rounds  fl(fl(dPer*(2+J))/(2-J)) + q  to FLOAT (:286-287).  One FMA with a = fl((2+J)/(2-J))
+                 * is within  e = 2^-49 (|dPer*a| + |q|)  of that double; if s-e and s+e round to the same float, so
+                 * does the reference's value (rounding is monotone) and the serial chain of a period is
+                 * float->double, FMA, double->float.  Otherwise (about once in 10^7 periods): the general period below. */
+                const double dJ = (double)dper, dS = (double)dsh;
+                const double aJ = itp[8][pj], aS = itp[10][ps];
+                const double sJ = __fma_rn(dJ, aJ, itp[3][pj]), sS = __fma_rn(dS, aS, itp[7][ps]);
+                const double eJ = __fma_rn(fabs(__dmul_rn(dJ, aJ)), 1.7763568394002505e-15, itp[9][pj]);
+                const double eS = __fma_rn(fabs(__dmul_rn(dS, aS)), 1.7763568394002505e-15, itp[11][ps]);
+                const float curJ = __double2float_rn(sJ), curS = __double2float_rn(sS);
+                const bool dj = !(__double2float_rn(__dsub_rn(sJ, eJ)) == __double2float_rn(__dadd_rn(sJ, eJ)));
+                const bool ds = !(__double2float_rn(__dsub_rn(sS, eS)) == __double2float_rn(__dadd_rn(sS, eS)));
                 const float Tf = ceilf(__fadd_rn(Pf, curJ));
                 const float An = __fadd_rn(ampf, curS);
                 if (dj || ds || Tf > t_hi || Tf < t_lo || !(Tf >= 1.0f && Tf <= 32767.0f) || An > a_hi || An < a_lo) break;
