@@ -120,7 +120,7 @@ typedef struct vs_timing {
 
 /* ---- options (vs_ctx_set_option) ------------------------------------------------------------ */
 #define VS_OPT_CHUNK_SAMPLES   1  /* time-chunk length; 0 = auto (fill the SMs), <0 = never chunk      */
-#define VS_OPT_CARRY_TOL       2  /* relative size the free response must decay to during warm-up (1e-13) */
+#define VS_OPT_CARRY_TOL       2  /* relative size the free response must decay to during warm-up (1e-12) */
 #define VS_OPT_EXACT_FILTER    3  /* 1: unfused mul+sub in the reference's order (bit-exact, 2x FP64 work, no chunking) */
 #define VS_OPT_SLAB_STREAMS    4  /* streams per launch/copy slab for host outputs; 0 = auto            */
 #define VS_OPT_TARGET_WARPS    5  /* auto-chunking aims at this many warps per SM sub-partition (2)      */

@@ -87,6 +87,7 @@ struct Slot {
     std::vector<size_t> plan_slab_c0, plan_slab_r0;
     uint64_t plan_tab_total = 0, plan_warm_total = 0;
     uint64_t plan_version = 1, uploaded_version[VS_DEPTH] = {};        /* which plan the device copies of chunks/order hold (0 = none) */
+    std::chrono::steady_clock::time_point last_enqueue{};
     uint64_t plan_for_version = 0;                   /* vs_ctx::in_version of the inputs the plan was made (or confirmed) for */
     uint64_t streams_version[VS_DEPTH] = {};         /* which inputs the device copies of the stream descriptors hold          */
 };
@@ -96,7 +97,7 @@ struct Slot {
 struct vs_ctx {
     std::vector<Slot> slots;
     double opt_chunk = 0;        /* 0 auto, <0 never, >0 fixed */
-    double opt_tol = 1e-13;
+    double opt_tol = 1e-12;      /* x |state| <= ~2e5 at the default gain: 2e-7 before quantisation, 50 x under the 1e-5 bar */
     int opt_plan_warps = -1;     /* -1 auto, 0 one thread per stream, 1 one warp per stream */
     int opt_exact = 0;
     int opt_slab = 0;
@@ -1065,8 +1066,13 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 bool plan_warps;
                 if (ctx->opt_plan_warps >= 0) plan_warps = ctx->opt_plan_warps != 0;
                 else {
-                    const bool busy = cudaEventQuery(sl.call_done[(cp + VS_DEPTH - 1u) % VS_DEPTH]) == cudaErrorNotReady;
+                    /* "in flight" = the previous call has not finished, or it was enqueued less than 2 ms ago (a
+                     * loop of calls whose host side momentarily fell behind the GPU is still a pipeline) */
+                    bool busy = cudaEventQuery(sl.call_done[(cp + VS_DEPTH - 1u) % VS_DEPTH]) == cudaErrorNotReady;
                     (void)cudaGetLastError();
+                    const auto now = std::chrono::steady_clock::now();
+                    if (std::chrono::duration<double, std::milli>(now - sl.last_enqueue).count() < 2.0) busy = true;
+                    sl.last_enqueue = now;
                     plan_warps = pa.n_streams <= (busy ? VS_PLAN_WARP_MAX : any_noise ? VS_PLAN_WARP_MAX_NOISE : VS_PLAN_WARP_MAX_IDLE);
                 }
                 CU(vs_launch_plan(pa, want_log, plan_warps, pstream));
