@@ -64,6 +64,7 @@ struct Slot {
     cudaStream_t plans[2] = {nullptr, nullptr};      /* descriptor upload + plan kernel; calls alternate between the two */
     cudaEvent_t call_done[VS_DEPTH] = {};            /* everything of the call that used ring slot p has finished (compute) */
     cudaEvent_t plan_done[VS_DEPTH] = {};
+    cudaEvent_t render_done[VS_DEPTH] = {};
     unsigned call_parity = 0;
     cudaEvent_t slab_done[2] = {nullptr, nullptr};   /* D2H of the slab using pcm[k] finished */
     cudaEvent_t slab_ready = nullptr;                /* render of the current slab finished   */
@@ -437,6 +438,15 @@ struct Batch {
     vs_period_log *log;
 };
 
+/* SMs the render kernel leaves to the plan kernels of the next calls.  A plan CTA keeps an SM for one plan time; the
+ * plan of a step takes a little longer than its render (measured: 1.2x on the bench workload and on the noise
+ * grid), so 1.5 SMs per plan CTA -- two plans partly side by side -- keep the plans ahead of the renders.  Large
+ * batches get none: their plan needs every SM anyway and simply alternates with the render. */
+int vs_plan_reserve(int plan_ctas)
+{
+    return 2 * plan_ctas <= VS_PLAN_SMS ? (3 * plan_ctas + 1) / 2 : 0;
+}
+
 /* Choose the time-chunk length for a group of streams (SURVEY.md 7 "Occupancy").
  * Filtering modes: the FP64 pipe of an SM sub-partition is saturated by ONE consumer warp, so the
  * kernel time is  waves * (L + warm-up)  sample-steps with  waves = ceil(warps / (SMs*4));  every
@@ -496,7 +506,7 @@ void plan_filter_chunks(vs_ctx *ctx, const Slot &slot, const std::vector<VsStrea
     /* rows per wave; a few SMs stay free for the plan kernels of the next two calls (one CTA of VS_PLAN_NT streams per
      * SM each, see VS_PLAN_SMEM) */
     const int plan_ctas = (int)((ns + VS_PLAN_NT - 1) / VS_PLAN_NT);
-    const int reserve = 2 * plan_ctas <= VS_PLAN_SMS ? 2 * plan_ctas : 0;       /* large batches: the plan needs every SM anyway */
+    const int reserve = vs_plan_reserve(plan_ctas);
     const int render_sms = slot.sm_count > 4 * VS_PLAN_SMS ? slot.sm_count - reserve : slot.sm_count;
     const double cap = (double)render_sms * VS_NT;
     /* streams of equal (length, preset) get equal chunk counts: plan over the distinct classes */
@@ -1154,7 +1164,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                  * flow-only kernel is small, a few of its CTAs share an SM */
                 const uint32_t blocks = (ra.n_rows / 32u + 3u) / 4u;
                 const int plan_ctas = (int)((ns + VS_PLAN_NT - 1) / VS_PLAN_NT);
-                const int reserve = 2 * plan_ctas <= VS_PLAN_SMS ? 2 * plan_ctas : 0;       /* large batches: the plan needs every SM anyway */
+                const int reserve = vs_plan_reserve(plan_ctas);
                 const uint32_t sms = (uint32_t)std::max(1, sl.sm_count - reserve);
                 uint32_t per_sm = 1;
                 if (b.mode == VS_MODE_FLOW) per_sm = std::max(1u, std::min(4u, (220u * 1024u) / (4u * ra.warp_bytes + (any_noise ? 16u * 1024u : 0u) + 1024u)));
@@ -1206,10 +1216,14 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             CU(cudaMemcpyAsync(b.log->rec + log_lo, sl.log.p, (log_hi - log_lo) * sizeof(vs_period_rec), cudaMemcpyDeviceToHost, sl.compute));
         if (want_log && b.log->count)
             CU(cudaMemcpyAsync(sl.h_nper[cp].p, sl.nper[cp].p, ns * sizeof(uint32_t), cudaMemcpyDeviceToHost, sl.compute));
-        CU(cudaMemcpyAsync(sl.h_status[cp].p, sl.status[cp].p, sizeof(int32_t), cudaMemcpyDeviceToHost, sl.compute));
         if (!out_dev) sl.scratch_parity = (unsigned)((sl.scratch_parity + n_slabs) & 1);
         if (g == 0) { cudaEvent_t t_last = timing_event(sl); CU(cudaEventRecord(t_last, sl.compute)); }
-        CU(cudaEventRecord(sl.call_done[cp], sl.compute));            /* parity-cp buffers are free once this fires */
+        /* the device's error flag comes home on the copy stream: nothing sits between this call's render kernel and
+         * the next call's on the compute stream */
+        CU(cudaEventRecord(sl.render_done[cp], sl.compute));
+        CU(cudaStreamWaitEvent(sl.copy, sl.render_done[cp], 0));
+        CU(cudaMemcpyAsync(sl.h_status[cp].p, sl.status[cp].p, sizeof(int32_t), cudaMemcpyDeviceToHost, sl.copy));
+        CU(cudaEventRecord(sl.call_done[cp], sl.copy));               /* parity-cp buffers are free once this fires */
     }
 
     prof.mark("launches enqueued");
@@ -1306,6 +1320,7 @@ int vs_ctx_create(vs_ctx **out, const int *devices, int n_devices, uint32_t flag
                   true;
         for (int k = 0; ok && k < VS_DEPTH; k++)
             ok = cudaEventCreateWithFlags(&s.call_done[k], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&s.render_done[k], cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&s.plan_done[k], cudaEventDisableTiming) == cudaSuccess;
         ctx->slots.push_back(s);
         if (!ok) { cudaGetLastError(); vs_ctx_destroy(ctx); return VS_ECUDA; }
@@ -1336,6 +1351,7 @@ void vs_ctx_destroy(vs_ctx *ctx)
         for (int k = 0; k < VS_DEPTH; k++) {
             if (s.call_done[k]) cudaEventDestroy(s.call_done[k]);
             if (s.plan_done[k]) cudaEventDestroy(s.plan_done[k]);
+            if (s.render_done[k]) cudaEventDestroy(s.render_done[k]);
         }
         for (int k = 0; k < 2; k++) if (s.plans[k]) cudaStreamDestroy(s.plans[k]);
         if (s.slab_done[0]) cudaEventDestroy(s.slab_done[0]);
