@@ -7,15 +7,21 @@ NVFLAGS   := -O3 -std=c++17 $(ARCH) -lineinfo -fmad=false -cudart static \
 LIBDIR    := voice_synth_b200/lib
 LIB       := $(LIBDIR)/libvoicesynth_cuda.so
 CSRC      := voice_synth_b200/csrc
-SRCS      := $(CSRC)/vs_api.cu $(CSRC)/vs_plan.cu $(CSRC)/vs_render.cu
+SRCS      := $(CSRC)/vs_api.cu $(CSRC)/vs_plan.cu $(CSRC)/vs_render.cu $(CSRC)/vs_flow_rows.cu
+OBJDIR    := build/obj
+OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(SRCS))
 HDRS      := include/voicesynth.h $(CSRC)/vs_internal.h $(CSRC)/vs_presets.h $(CSRC)/vs_device.cuh
 
 all: lib host oracle
 
-lib: $(LIB)
-$(LIB): $(SRCS) $(HDRS)
+lib:
+	$(MAKE) -j4 $(LIB)
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
+	mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c -o $@ $<
+$(LIB): $(OBJS)
 	mkdir -p $(LIBDIR)
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRCS)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(OBJS)
 
 host: lib
 	$(MAKE) -C host

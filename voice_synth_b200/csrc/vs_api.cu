@@ -35,6 +35,8 @@ cudaError_t vs_launch_render(const VsRenderArgs &a, int mode, int gen, bool nois
 cudaError_t vs_render_init_device();
 int vs_render_window(int mode);
 int vs_render_tiles(int mode);
+cudaError_t vs_launch_flow_rows(const VsRenderArgs &a, cudaStream_t s);
+int vs_flow_rows_warps(void);
 cudaError_t vs_launch_fp64_peak(double *scratch, int blocks, int iters, cudaStream_t s);
 cudaError_t vs_launch_vnoise(int16_t *pcm, const VsNoiseRow *rows, uint32_t n_rows, cudaStream_t s);
 
@@ -69,7 +71,7 @@ struct Slot {
     cudaEvent_t slab_done[2] = {nullptr, nullptr};   /* D2H of the slab using pcm[k] finished */
     cudaEvent_t slab_ready = nullptr;                /* render of the current slab finished   */
     DevBuf streams[VS_DEPTH], chunks[VS_DEPTH], order[VS_DEPTH], table[VS_DEPTH], snap[VS_DEPTH], nper[VS_DEPTH], status[VS_DEPTH];
-    DevBuf costab, pcm[2], raw[2], flowin[2], log;
+    DevBuf costab, pcm[2], raw[2], flowin[2], log, ticket;
     PinBuf h_streams[VS_DEPTH], h_chunks[VS_DEPTH], h_order[VS_DEPTH], h_nper[VS_DEPTH], h_status[VS_DEPTH];
     size_t costab_uploaded = 0;
     std::vector<cudaEvent_t> tev;                    /* timing events (slot 0 only) */
@@ -125,7 +127,7 @@ struct vs_ctx {
     struct Facts {
         uint64_t max_n = 0;
         bool any_noise = false, any_kvar = false, int_filter = true, amp_fits = true, noise_simple = true;
-        int t_min = 0x7fffffff, t_max = 0;
+        int t_min = 0x7fffffff, t_max = 0, t2_min = 0x7fffffff;
     } in_facts;
     uint64_t in_version = 0;     /* bumped whenever in_hs changes */
     bool env_profile_host = false, env_sync_plan = false;
@@ -386,6 +388,7 @@ uint32_t pulse_table_for(vs_ctx *ctx, int T2, float K)
     if (it != ctx->pulse_index.end()) off = it->second;
     else {
         const uint32_t src = cos_table_for(ctx, T2);                  /* h then c; may grow cos_host */
+        if (ctx->cos_host.size() & 1) ctx->cos_host.push_back(0.0);   /* 16-byte aligned */
         off = (uint32_t)ctx->cos_host.size();
         for (int i = 0; i < T2; i++) { const double h = ctx->cos_host[src + i]; ctx->cos_host.push_back(h); }
         const double Kd = (double)K;
@@ -396,6 +399,13 @@ uint32_t pulse_table_for(vs_ctx *ctx, int T2, float K)
             const double fv = f;
             ctx->cos_host.push_back(fv);
         }
+        /* for vs_flow_rows_kernel, which reads two neighbouring entries with one 16-byte load: two zeros (the closed
+         * phase), then the same table again moved up by one entry, so that a pair is 16-byte aligned in one of the two
+         * copies whatever its parity */
+        const size_t n2 = 2 * (size_t)T2;
+        ctx->cos_host.push_back(0.0);
+        ctx->cos_host.push_back(0.0);
+        for (size_t k = 0; k < n2 + 2; k++) { const double v = k + 1 < n2 + 2 ? ctx->cos_host[off + k + 1] : 0.0; ctx->cos_host.push_back(v); }
         ctx->pulse_index[key] = off;
     }
     ctx->pulse_last_key = key;
@@ -452,10 +462,19 @@ int vs_plan_reserve(int plan_ctas)
  * kernel time is  waves * (L + warm-up)  sample-steps with  waves = ceil(warps / (SMs*4));  every
  * chunk but the first pays the warm-up again.  Pick the chunk count per stream that minimises it.
  * Flow mode has no carry, chunks are free: aim at `8*opt_warps` warps per sub-partition. */
-uint32_t choose_chunk(vs_ctx *ctx, const Slot &slot, int mode, size_t n_streams, uint64_t total, double avg_warm)
+uint32_t choose_chunk(vs_ctx *ctx, const Slot &slot, int mode, size_t n_streams, uint64_t total, double avg_warm, bool flow_rows)
 {
     if (ctx->opt_chunk < 0) return 0;
     if (mode != VS_MODE_FLOW && ctx->opt_exact) return 0;
+    if (flow_rows) {
+        /* lanes along the row (vs_flow_rows_kernel): a warp takes a row at a time, 256 samples per step, rows handed out
+         * by a ticket -- about eight rows per warp balance the SMs and keep the cost of opening a row (its descriptors,
+         * the first batch of periods) small */
+        double L = ctx->opt_chunk > 0 ? ctx->opt_chunk : std::ceil((double)total / ((double)slot.sm_count * 4.0 * vs_flow_rows_warps() * 8.0));
+        if (L < 512.0) L = 512.0;
+        if (L > 1048576.0) L = 1048576.0;
+        return ((uint32_t)L + 255u) & ~255u;
+    }
     if (ctx->opt_chunk > 0) {
         uint32_t L = (uint32_t)ctx->opt_chunk;
         L = (L + 7u) & ~7u;
@@ -606,7 +625,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
     const PtrKind out_kind = classify(b.pcm_out, &odev);
     {   /* what the chunk plan depends on besides the parameter arrays */
         const double key[10] = {ctx->opt_chunk, ctx->opt_tol, (double)ctx->opt_exact, (double)ctx->opt_slab, ctx->opt_warps, (double)ctx->opt_simple_gen,
-                                (double)(out_kind == PK_DEVICE), (double)(reinterpret_cast<uintptr_t>(b.pcm_out) & 15), (double)ctx->slots.size(), 0.0};
+                                (double)(out_kind == PK_DEVICE), (double)(reinterpret_cast<uintptr_t>(b.pcm_out) & 127), (double)ctx->slots.size(), 0.0};
         snapshot_inputs(b, want_log, key, sizeof key, blob);
     }
     const bool same_inputs = blob.size() == ctx->in_blob.size() && memcmp(blob.data(), ctx->in_blob.data(), blob.size()) == 0;
@@ -618,6 +637,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
     bool any_noise = false, any_kvar = false;
     bool int_filter = true;          /* every stream: integral gain, pre-emphasis 0 or 1 -> both commute to the integer input */
     int t_min = 0x7fffffff, t_max = 0;   /* bounds on the pitch period lengths of the batch */
+    int t2_min = 0x7fffffff;             /* shortest half open phase */
     bool amp_fits = true;            /* no amplitude can pass 32767 (fast generator) */
     bool noise_simple = true;        /* every noisy stream has DC <= 1 (then T4 == 0) and T2 >= 16: 16-byte period entries do */
     for (size_t i = 0; i < n; i++) {
@@ -636,6 +656,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             s.P = P;
             s.T2 = row_T2(r, s.P);
             s.cos_off = cos_table_for(ctx, s.T2);
+            t2_min = std::min(t2_min, (int)s.T2);
             any_kvar |= r.Kvar != 0.0f;
             s.amp = r.amp; s.DC = r.DC; s.jitter = r.jitter; s.shimmer = r.shimmer; s.K = r.K; s.Kvar = r.Kvar;
             s.noise = r.noise; s.seed = r.seed; s.flags = r.flags;
@@ -694,7 +715,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
     }
     vs_ctx::Facts &fc = ctx->in_facts;
     fc.max_n = max_n; fc.any_noise = any_noise; fc.any_kvar = any_kvar; fc.int_filter = int_filter; fc.amp_fits = amp_fits;
-    fc.noise_simple = noise_simple; fc.t_min = t_min; fc.t_max = t_max;
+    fc.noise_simple = noise_simple; fc.t_min = t_min; fc.t_max = t_max; fc.t2_min = t2_min;
     ctx->in_blob.swap(blob);
     ctx->in_version++;
     }
@@ -745,6 +766,9 @@ int run_batch(vs_ctx *ctx, const Batch &b)
     const bool exact = ctx->opt_exact != 0;
     /* period table format: 8-byte entries (amplitude, length) where they suffice, 16-byte ones for plain glottal noise */
     const int compact = (any_kvar || want_log) ? VS_TAB_FULL : !any_noise ? VS_TAB_C8 : noise_simple ? VS_TAB_N16 : VS_TAB_FULL;
+    /* flow without glottal noise: lanes along the row (vs_flow_rows_kernel).  T2 >= 2: row_validate() bounds A*K then */
+    const bool flow_rows = b.mode == VS_MODE_FLOW && compact == VS_TAB_C8 && amp_fits && !ctx->opt_simple_gen && t_min >= 24 && fc.t2_min >= 2;
+    const uint64_t ph_mask = flow_rows ? 63u : 7u;           /* rows keep their position inside a 128-byte line / a 16-byte piece */
 
     /* ---- 4. per slot: descriptors up, then slabs of plan -> render -> copy ------------------- */
     for (size_t g = 0; g < nslots; g++) {
@@ -787,7 +811,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         { double t = ctx->opt_tol, w = ctx->opt_warps; uint64_t u; memcpy(&u, &t, 8); sig.push_back(u); memcpy(&u, &w, 8); sig.push_back(u); }
         for (size_t i = s0; i < s1; i++) {
             const uint64_t base_addr = out_dev ? (reinterpret_cast<uintptr_t>(b.pcm_out) >> 1) + hs[i].out_off : hs[i].out_off;
-            sig.push_back((uint64_t)hs[i].n | ((uint64_t)hs[i].preset << 32) | ((base_addr & 7) << 40));
+            sig.push_back((uint64_t)hs[i].n | ((uint64_t)hs[i].preset << 32) | ((base_addr & ph_mask) << 40));
             sig.push_back((uint64_t)hs[i].tab_cap | ((uint64_t)hs[i].pulse_off << 32));          /* row order and table cache depend on these */
             sig.push_back((uint64_t)(uint32_t)hs[i].T2 | ((uint64_t)hs[i].tpad << 32));
         }
@@ -805,7 +829,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             const size_t a0 = s0 + k * slab_streams, a1 = std::min(s1, a0 + slab_streams);
             uint64_t tot = 0;
             for (size_t i = a0; i < a1; i++) tot += hs[i].n;
-            const uint32_t Lflow = b.mode == VS_MODE_FLOW ? choose_chunk(ctx, sl, b.mode, a1 - a0, tot, 0.0) : 0u;
+            const uint32_t Lflow = b.mode == VS_MODE_FLOW ? choose_chunk(ctx, sl, b.mode, a1 - a0, tot, 0.0, flow_rows) : 0u;
             std::vector<uint32_t> nch;
             if (b.mode != VS_MODE_FLOW) plan_filter_chunks(ctx, sl, hs, a0, a1, nch);
             slab_c0[k] = hc.size();
@@ -814,9 +838,10 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 const uint64_t base_addr = out_dev ? (reinterpret_cast<uintptr_t>(b.pcm_out) >> 1) + s.out_off : s.out_off;
                 /* host outputs are mirrored on the device at the same offsets relative to a 16-byte
                  * aligned slab base, so the phase of a row is its sample offset mod 8 either way */
-                const uint32_t ph = (uint32_t)(base_addr & 7);
+                const uint32_t ph = (uint32_t)(base_addr & ph_mask);
                 const uint32_t W = (b.mode == VS_MODE_FLOW) ? 0u : (uint32_t)ctx->warm[s.preset];
-                /* chunk c > 0 emits [L0 + (c-1)*L - ph, L0 + c*L - ph); L0 and L are multiples of 8 */
+                /* chunk c > 0 emits [L0 + (c-1)*L - ph, L0 + c*L - ph); L0 and L are multiples of 8 (of 256 for the
+                 * lanes-along-the-row flow kernel, whose steps then never straddle two chunks) */
                 uint32_t C, L, L0;
                 if (b.mode == VS_MODE_FLOW) {
                     L = L0 = Lflow;
@@ -998,7 +1023,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 gm.in_min = std::min(gm.in_min, hs[i].in_off);
                 gm.in_max = std::max(gm.in_max, hs[i].in_off + hs[i].n);
             }
-            gm.out_min &= ~7ull;                                      /* keep (offset mod 8) on the device */
+            gm.out_min &= ~63ull;                                     /* keep (offset mod 64) on the device */
             gm.in_min &= ~7ull;
             geom[k] = gm;
             span_max = std::max(span_max, gm.out_max - gm.out_min);
@@ -1006,7 +1031,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         }
         if (!out_dev) {
             for (int d = 0; d < 2; d++) {
-                if ((rc = dev_reserve(ctx, sl, sl.pcm[d], span_max * sizeof(int16_t) + 64))) return rc;
+                if ((rc = dev_reserve(ctx, sl, sl.pcm[d], span_max * sizeof(int16_t) + 256))) return rc;
                 if (b.raw_out && (rc = dev_reserve(ctx, sl, sl.raw[d], span_max * sizeof(double) + 64))) return rc;
                 if (b.mode == VS_MODE_FILTER && (rc = dev_reserve(ctx, sl, sl.flowin[d], in_span_max * sizeof(int16_t) + 64))) return rc;
             }
@@ -1160,6 +1185,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                     ra.warp_bytes = wbytes; ra.ring_R = R; ra.ring_fetch = per_win + 2u; ra.ring_ahead = ahead; ra.cache_doubles = cache;
                 }
             }
+            uint32_t render_sms = 1;
             {   /* persistent grid: one CTA per render SM (the plan kernels of the next calls own the others); the
                  * flow-only kernel is small, a few of its CTAs share an SM */
                 const uint32_t blocks = (ra.n_rows / 32u + 3u) / 4u;
@@ -1169,11 +1195,21 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 uint32_t per_sm = 1;
                 if (b.mode == VS_MODE_FLOW) per_sm = std::max(1u, std::min(4u, (220u * 1024u) / (4u * ra.warp_bytes + (any_noise ? 16u * 1024u : 0u) + 1024u)));
                 ra.grid = std::min(blocks, sms * per_sm);
+                render_sms = sms;
             }
             const int filt = exact ? VS_FILT_EXACT : ((int_filter && !b.raw_out) ? VS_FILT_INT : VS_FILT_FMA);
-            CU(vs_launch_render(ra, b.mode, gen, any_noise, filt, sl.compute));
+            if (flow_rows) {
+                if ((rc = dev_reserve(ctx, sl, sl.ticket, 256))) return rc;
+                CU(cudaMemsetAsync(sl.ticket.p, 0, sizeof(uint32_t), sl.compute));
+                ra.ticket = (uint32_t *)sl.ticket.p;
+                const uint32_t rows_per_cta = (uint32_t)vs_flow_rows_warps();
+                ra.grid = std::max(1u, std::min((ra.n_rows + rows_per_cta - 1u) / rows_per_cta, render_sms * 4u));
+                CU(vs_launch_flow_rows(ra, sl.compute));
+            } else
+                CU(vs_launch_render(ra, b.mode, gen, any_noise, filt, sl.compute));
             ctx->timing.launches++;
-            ctx->timing.render_path = (gen == VS_GEN_FAST ? 1u : 0u) | (any_noise ? 2u : 0u) | ((uint32_t)(b.raw_out && filt == VS_FILT_INT ? VS_FILT_FMA : filt) << 2);
+            ctx->timing.render_path = (gen == VS_GEN_FAST || flow_rows ? 1u : 0u) | (any_noise ? 2u : 0u) | ((uint32_t)(b.raw_out && filt == VS_FILT_INT ? VS_FILT_FMA : filt) << 2) |
+                                      (flow_rows ? 32u : 0u);
             if (g == 0) { cudaEvent_t e2 = timing_event(sl); CU(cudaEventRecord(e2, sl.compute)); }
 
             if (!out_dev) {
