@@ -72,6 +72,7 @@ struct Slot {
     cudaEvent_t slab_ready = nullptr;                /* render of the current slab finished   */
     DevBuf streams[VS_DEPTH], chunks[VS_DEPTH], order[VS_DEPTH], table[VS_DEPTH], snap[VS_DEPTH], nper[VS_DEPTH], status[VS_DEPTH];
     DevBuf costab, pcm[2], raw[2], flowin[2], log, ticket;
+    uint32_t ticket_base = 0;                        /* value of the row counter of vs_flow_rows_kernel before the next launch */
     PinBuf h_streams[VS_DEPTH], h_chunks[VS_DEPTH], h_order[VS_DEPTH], h_nper[VS_DEPTH], h_status[VS_DEPTH];
     size_t costab_uploaded = 0;
     std::vector<cudaEvent_t> tev;                    /* timing events (slot 0 only) */
@@ -468,9 +469,10 @@ uint32_t choose_chunk(vs_ctx *ctx, const Slot &slot, int mode, size_t n_streams,
     if (mode != VS_MODE_FLOW && ctx->opt_exact) return 0;
     if (flow_rows) {
         /* lanes along the row (vs_flow_rows_kernel): a warp takes a row at a time, 256 samples per step, rows handed out
-         * by a ticket -- about eight rows per warp balance the SMs and keep the cost of opening a row (its descriptors,
-         * the first batch of periods) small */
-        double L = ctx->opt_chunk > 0 ? ctx->opt_chunk : std::ceil((double)total / ((double)slot.sm_count * 4.0 * vs_flow_rows_warps() * 8.0));
+         * by a ticket -- about four rows per warp balance the SMs and keep the cost of opening a row (its descriptors,
+         * the first batch of periods: five dependent memory round trips) small.  Measured on the bench batch: 2.6 / 3.5 /
+         * 5.2 / 7.8 rows per warp = 0.078 / 0.076 / 0.078 / 0.080 ms */
+        double L = ctx->opt_chunk > 0 ? ctx->opt_chunk : std::ceil((double)total / ((double)slot.sm_count * 4.0 * vs_flow_rows_warps() * 4.0));
         if (L < 512.0) L = 512.0;
         if (L > 1048576.0) L = 1048576.0;
         return ((uint32_t)L + 255u) & ~255u;
@@ -1199,12 +1201,17 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             }
             const int filt = exact ? VS_FILT_EXACT : ((int_filter && !b.raw_out) ? VS_FILT_INT : VS_FILT_FMA);
             if (flow_rows) {
-                if ((rc = dev_reserve(ctx, sl, sl.ticket, 256))) return rc;
-                CU(cudaMemsetAsync(sl.ticket.p, 0, sizeof(uint32_t), sl.compute));
+                if (!sl.ticket.p) {
+                    if ((rc = dev_reserve(ctx, sl, sl.ticket, 256))) return rc;
+                    CU(cudaMemsetAsync(sl.ticket.p, 0, 256, sl.compute));
+                    sl.ticket_base = 0;
+                }
                 ra.ticket = (uint32_t *)sl.ticket.p;
+                ra.ticket_base = sl.ticket_base;
                 const uint32_t rows_per_cta = (uint32_t)vs_flow_rows_warps();
                 ra.grid = std::max(1u, std::min((ra.n_rows + rows_per_cta - 1u) / rows_per_cta, render_sms * 4u));
                 CU(vs_launch_flow_rows(ra, sl.compute));
+                sl.ticket_base += ra.n_rows + ra.grid * rows_per_cta;       /* wraps like the device counter does */
             } else
                 CU(vs_launch_render(ra, b.mode, gen, any_noise, filt, sl.compute));
             ctx->timing.launches++;

@@ -47,9 +47,9 @@ __global__ void __launch_bounds__(VS_FLOWROWS_WARPS * 32, 4) vs_flow_rows_kernel
 
     for (;;) {
         uint32_t row = 0;
-        if (lane == 0) row = atomicAdd(a.ticket, 1u);
+        if (lane == 0) row = atomicAdd(a.ticket, 1u) - a.ticket_base;
         row = __shfl_sync(VS_FULL, row, 0);
-        if (row >= a.n_rows) break;
+        if (row >= a.n_rows) break;                         /* (every warp draws exactly one ticket beyond the last row) */
         const uint32_t chunk_id = __ldg(a.order + row);
         if (chunk_id == VS_NO_CHUNK) continue;
         const uint4 c0 = __ldg(reinterpret_cast<const uint4 *>(a.chunks + chunk_id));        /* stream, emit_lo, emit_hi, gen_target */
@@ -169,7 +169,8 @@ __global__ void __launch_bounds__(VS_FLOWROWS_WARPS * 32, 4) vs_flow_rows_kernel
     }
 }
 
-/* the lanes-along-the-row flow kernel: grid CTAs of VS_FLOWROWS_WARPS warps; *a.ticket must be 0 */
+/* the lanes-along-the-row flow kernel: grid CTAs of VS_FLOWROWS_WARPS warps.  The ticket counter is never reset: a
+ * launch starts at a.ticket_base and leaves it at ticket_base + n_rows + (warps of the grid) */
 cudaError_t vs_launch_flow_rows(const VsRenderArgs &a, cudaStream_t s)
 {
     vs_flow_rows_kernel<<<a.grid, VS_FLOWROWS_WARPS * 32, 0, s>>>(a);

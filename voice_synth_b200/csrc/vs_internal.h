@@ -135,7 +135,8 @@ struct VsRenderArgs {
     uint32_t        ring_ahead;     /* how far beyond the current period the ring is kept filled     */
     uint32_t        cache_doubles;  /* pulse-table cache per warp                                    */
     uint32_t        debug;          /* timing experiments (VS_OPT_DEBUG): bit 0 = skip the bulk stores */
-    uint32_t       *ticket;         /* vs_flow_rows_kernel: next row to hand out (zero at launch)    */
+    uint32_t       *ticket;         /* vs_flow_rows_kernel: the counter rows are handed out by ...   */
+    uint32_t        ticket_base;    /* ... and its value when the launch starts                      */
 };
 
 /* vowel -n (N1): one entry per stream */
