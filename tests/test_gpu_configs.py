@@ -217,6 +217,77 @@ def test_fast_paths_fuzz(ctx, vs, oracle):
             assert int(np.abs(pcm.astype(np.int32) - pcm2.astype(np.int32)).max()) <= 1
 
 
+def test_flow_rows_kernel_layouts(ctx, vs, oracle):
+    """vs_flowgen_batch without glottal noise runs on the warp-per-row kernel (lanes along the row): ragged rows at
+    odd offsets with gaps, pitch periods from 30 to 560 samples, streams shorter than one 256-sample step, DC offsets,
+    host and device buffers at every phase of a 128-byte line, chunked and not -- every stream bit for bit"""
+    import torch
+    rng = np.random.default_rng(4242)
+    n = 160
+    args, seeds = [], []
+    for i in range(n):
+        f0 = float(np.exp(rng.uniform(np.log(50.0), np.log(580.0))))
+        a = ["-d", f"{rng.uniform(0.5, 1.7):.4f}", "-f", f"{f0:.2f}", "-g", f"{f0 * 1.2 + 10:.2f}"]
+        if rng.random() < 0.7:
+            a += ["-j", f"{rng.uniform(0, 5):.2f}"]
+        if rng.random() < 0.7:
+            a += ["-s", f"{rng.uniform(0, 15):.2f}"]
+        if rng.random() < 0.5:
+            a += ["-c", f"{rng.uniform(0.2, 1.0):.3f}"]
+        if rng.random() < 0.5:
+            a += ["-k", f"{rng.uniform(0.5, 3):.3f}"]
+        if rng.random() < 0.3:
+            a += ["-l", f"{rng.uniform(0, 0.3):.3f}"]
+        if rng.random() < 0.4:
+            a += ["-a", str(int(rng.integers(1, 18000)))]
+        args.append(a)
+        seeds.append(int(rng.integers(0, 2**32)))
+    p = vs.FlowParams.from_cli(args, seeds)
+    # the ABI takes any positive duration (the tool's usage() wants 0.5 s): rows shorter than a step, than a line
+    for i in range(0, n, 3):
+        p.dur[i] = np.float32([0.0005, 0.003, 0.011, 0.05, 0.3][(i // 3) % 5] * rng.uniform(0.8, 1.2))
+    ns = vs.flow_nsamples(p)
+    assert int(ns.min()) < 32 and int(ns.max()) > 30000
+    # ragged layout: a gap of 0..70 samples in front of every row, so rows start at every phase of a line
+    gaps = rng.integers(0, 71, n).astype(np.uint64)
+    offs = (np.concatenate([[0], np.cumsum(ns + gaps)[:-1]]) + gaps).astype(np.uint64)
+    total = int(offs[-1] + ns[-1]) + 64
+    want = [oracle.flowgen(_opar(oracle, vs, p, i)) for i in range(n)]
+    for chunk in (0, 512, 1000, -1):
+        ctx.set_option(vs.OPT_CHUNK_SAMPLES, chunk)
+        try:
+            for shift in (0, 1, 37):
+                host = np.full(total + shift, -12345, dtype=np.int16)
+                ctx.flowgen_batch(p, out=host[shift:], offsets=offs)
+                t = ctx.timing()
+                assert t["render_path"] & 32, "flow without noise must take the warp-per-row kernel"
+                dev = torch.full((total + shift,), -12345, dtype=torch.int16, device="cuda")
+                torch.cuda.synchronize()                      # (the library runs on its own streams)
+                ctx.flowgen_batch(p, out=dev[shift:], offsets=offs)
+                ctx.sync()
+                got_dev = dev.cpu().numpy()
+                used = np.zeros(total + shift, dtype=bool)
+                for i in range(n):
+                    a0 = shift + int(offs[i])
+                    used[a0: a0 + int(ns[i])] = True
+                    assert np.array_equal(host[a0: a0 + int(ns[i])], want[i]), f"host, chunk {chunk}, shift {shift}, stream {i}"
+                    assert np.array_equal(got_dev[a0: a0 + int(ns[i])], want[i]), f"device, chunk {chunk}, shift {shift}, stream {i}"
+                # nothing outside the rows is touched (device buffers are written in place)
+                assert np.all(got_dev[~used] == -12345), f"device, chunk {chunk}, shift {shift}: wrote outside the rows"
+        finally:
+            ctx.set_option(vs.OPT_CHUNK_SAMPLES, 0)
+    # the lane-per-row kernel (forced by the option) gives the same bytes
+    ctx.set_option(vs.OPT_SIMPLE_GEN, 1)
+    try:
+        host = np.zeros(total, dtype=np.int16)
+        ctx.flowgen_batch(p, out=host, offsets=offs)
+        assert not ctx.timing()["render_path"] & 32
+    finally:
+        ctx.set_option(vs.OPT_SIMPLE_GEN, 0)
+    for i in range(n):
+        assert np.array_equal(host[int(offs[i]): int(offs[i]) + int(ns[i])], want[i])
+
+
 def test_edge_shapes(ctx, vs, oracle):
     """ragged batch: shortest legal stream, very high and very low F0, a stream shorter than one window"""
     args = ["-d 0.5 -f 50 -g 60", "-d 0.5 -f 1000 -g 1100 -j 1 -s 1", "-d 0.5 -r 100 -f 50 -g 60 -s 2",
