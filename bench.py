@@ -466,7 +466,7 @@ def main():
                               "useful_tdfma_s": round(useful, 3), "frac_useful": round(useful / peak_dfma, 4),
                               "peak_at_sampled_clock_tdfma_s": round(peak_at_clock, 3) if peak_at_clock else None,
                               "frac_useful_at_sampled_clock": round(useful / peak_at_clock, 4) if peak_at_clock else None}},
-        "roofline_flow": {"bound": "hbm", "kernel": "vs_render_kernel<FLOW> via vs_flowgen_batch, same batch, PCM resident in HBM",
+        "roofline_flow": {"bound": "hbm", "kernel": "vs_flow_rows_kernel (a warp per row, lanes along the row) via vs_flowgen_batch, same batch, PCM resident in HBM",
                           "bytes_per_sample": 2, "render_ms": round(t_flow["render_ms"], 4), "plan_ms": round(t_flow["plan_ms"], 4),
                           "achieved": round(2.0 * samples_per_step / (t_flow["render_ms"] * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
                           "frac": round(2.0 * samples_per_step / (t_flow["render_ms"] * 1e-3) / 1e9 / peak, 4)},
