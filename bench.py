@@ -359,7 +359,7 @@ def main():
         p3, f3 = workloads.cfg3(n=8192, first=rank * 8192)
         n3 = int(api.flow_nsamples(p3).sum())
         out3 = torch.empty(n3, dtype=torch.int16, device="cuda")
-        for _ in range(3):
+        for _ in range(5):                  # (the first call of a new shape sizes the library's buffers)
             ctx.synth_batch(p3, f3, out=out3)
         ctx.sync()
         barrier()
@@ -371,7 +371,7 @@ def main():
         barrier()
         ms3 = e0.elapsed_time(e1) / k3
         t3 = ctx.timing()
-        launches += t3["launches"] * (k3 + 3)
+        launches += t3["launches"] * (k3 + 5)
         del out3
         # configs[4]: 1 M utterances x 1 s, 131 072 per GPU, PCM streamed to pinned host memory: eight calls of
         # 16 384 utterances alternate between two pinned buffers, PCIe inside the timed region

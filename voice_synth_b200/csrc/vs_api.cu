@@ -965,19 +965,45 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         cudaStream_t pstream = sl.plans[cp & 1u];
         CU(cudaEventSynchronize(sl.call_done[cp]));                   /* the call before the previous one is done with them */
         int rc;
-        const void *ps_before = sl.streams[cp].p;
-        if ((rc = dev_reserve(ctx, sl, sl.streams[cp], ns * sizeof(VsStream)))) return rc;
-        {
-            const void *pc = sl.chunks[cp].p, *po = sl.order[cp].p;
-            if ((rc = dev_reserve(ctx, sl, sl.chunks[cp], nc * sizeof(VsChunk)))) return rc;
-            if ((rc = dev_reserve(ctx, sl, sl.order[cp], nrows * sizeof(uint32_t) + 16))) return rc;
-            if (pc != sl.chunks[cp].p || po != sl.order[cp].p) sl.uploaded_version[cp] = 0;          /* reallocated */
-        }
-        if ((rc = dev_reserve(ctx, sl, sl.nper[cp], ns * sizeof(uint32_t)))) return rc;
-        if ((rc = dev_reserve(ctx, sl, sl.status[cp], sizeof(int32_t)))) return rc;
+        /* The descriptor / table buffers form a ring of VS_DEPTH sets.  When one of them has to grow, the same buffer of
+         * every set grows with it: a new batch shape pays for its memory in its FIRST call (growing means a device-wide
+         * synchronisation, cudaFree / cudaMalloc / cudaHostAlloc), not in each of its first VS_DEPTH calls. */
+        auto drain = [&]() -> int {
+            CU(cudaStreamSynchronize(sl.plans[0]));
+            CU(cudaStreamSynchronize(sl.plans[1]));
+            CU(cudaStreamSynchronize(sl.compute));
+            CU(cudaStreamSynchronize(sl.copy2));
+            CU(cudaStreamSynchronize(sl.copy));
+            return VS_OK;
+        };
+        auto ring_dev = [&](DevBuf (&ring)[VS_DEPTH], size_t bytes) -> int {
+            if (bytes <= ring[cp].cap) return VS_OK;
+            for (unsigned d = 0; d < VS_DEPTH; d++) {
+                const void *before = ring[d].p;
+                const int r = dev_reserve(ctx, sl, ring[d], bytes);
+                if (r) return r;
+                if (before != ring[d].p) { sl.uploaded_version[d] = 0; sl.streams_version[d] = 0; }   /* its contents are gone */
+            }
+            return VS_OK;
+        };
+        auto ring_pin = [&](PinBuf (&ring)[VS_DEPTH], size_t bytes) -> int {
+            if (bytes <= ring[cp].cap) return VS_OK;
+            const int r0 = drain();                                   /* copies of the calls in flight read from these */
+            if (r0) return r0;
+            for (unsigned d = 0; d < VS_DEPTH; d++) {
+                const int r = pin_reserve(ctx, ring[d], bytes);
+                if (r) return r;
+            }
+            return VS_OK;
+        };
+        if ((rc = ring_dev(sl.streams, ns * sizeof(VsStream)))) return rc;
+        if ((rc = ring_dev(sl.chunks, nc * sizeof(VsChunk)))) return rc;
+        if ((rc = ring_dev(sl.order, nrows * sizeof(uint32_t) + 16))) return rc;
+        if ((rc = ring_dev(sl.nper, ns * sizeof(uint32_t)))) return rc;
+        if ((rc = ring_dev(sl.status, sizeof(int32_t)))) return rc;
         if (b.mode != VS_MODE_FILTER) {
-            if ((rc = dev_reserve(ctx, sl, sl.table[cp], (tab_total + 8) * VS_TAB_ENTRY_BYTES(compact)))) return rc;
-            if (any_noise && (rc = dev_reserve(ctx, sl, sl.snap[cp], nc * 32 * sizeof(uint32_t)))) return rc;
+            if ((rc = ring_dev(sl.table, (tab_total + 8) * VS_TAB_ENTRY_BYTES(compact)))) return rc;
+            if (any_noise && (rc = ring_dev(sl.snap, nc * 32 * sizeof(uint32_t)))) return rc;
             if ((rc = dev_reserve(ctx, sl, sl.costab, (ctx->cos_host.size() + VS_COS_SLACK) * sizeof(double)))) return rc;
             if (sl.costab_uploaded != ctx->cos_host.size()) {
                 /* tables only ever grow; a synchronous copy keeps the host vector free to grow again */
@@ -992,11 +1018,11 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                 sl.costab_uploaded = ctx->cos_host.size();
             }
         }
-        if ((rc = pin_reserve(ctx, sl.h_streams[cp], ns * sizeof(VsStream)))) return rc;
-        if ((rc = pin_reserve(ctx, sl.h_chunks[cp], nc * sizeof(VsChunk)))) return rc;
-        if ((rc = pin_reserve(ctx, sl.h_order[cp], nrows * sizeof(uint32_t) + 16))) return rc;
-        if ((rc = pin_reserve(ctx, sl.h_nper[cp], ns * sizeof(uint32_t)))) return rc;
-        if ((rc = pin_reserve(ctx, sl.h_status[cp], sizeof(int32_t)))) return rc;
+        if ((rc = ring_pin(sl.h_streams, ns * sizeof(VsStream)))) return rc;
+        if ((rc = ring_pin(sl.h_chunks, nc * sizeof(VsChunk)))) return rc;
+        if ((rc = ring_pin(sl.h_order, nrows * sizeof(uint32_t) + 16))) return rc;
+        if ((rc = ring_pin(sl.h_nper, ns * sizeof(uint32_t)))) return rc;
+        if ((rc = ring_pin(sl.h_status, sizeof(int32_t)))) return rc;
 
         /* log span of this slot */
         uint64_t log_lo = 0, log_hi = 0;
@@ -1042,7 +1068,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         /* upload descriptors; the previous call on this slot must be done with the staging buffers
          * (everything above overlapped with it) */
         /* (the device copy of slot `cp` may still hold exactly these descriptors: three calls ago, same inputs) */
-        const bool upload_streams = sl.streams_version[cp] != ctx->in_version || ps_before != sl.streams[cp].p;
+        const bool upload_streams = sl.streams_version[cp] != ctx->in_version;     /* (0 after the buffer was reallocated) */
         VsStream *ps = (VsStream *)sl.h_streams[cp].p;
         for (size_t k = 0; upload_streams && k < n_slabs; k++) {
             const size_t a0 = s0 + k * slab_streams, a1 = std::min(s1, a0 + slab_streams);
