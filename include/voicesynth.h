@@ -178,6 +178,27 @@ int vs_vowel_filter_batch(vs_ctx *ctx, const int16_t *flow_in, const uint64_t *i
                           const uint64_t *nsamp, const vs_filter_params *f, size_t n,
                           int16_t *pcm_out, const uint64_t *out_offsets, double *raw_out);
 
+/* SURVEY 8f N4 -- cycle-to-cycle analysis of glottal flow (the measurements of the reference's `acoustic` tools,
+ * README:14-16; their code is not in the reference tree, so the definitions below are this library's own).
+ * Per stream, with thresholds lo[i] <= hi[i] (NULL: 0, the closed-phase level of a flow generated without -l):
+ *   a trigger, armed at the start and by every sample x <= lo, fires at the first sample x > hi while armed: an ONSET
+ *   (for noise-free flow with lo = hi = (short)DC: the second sample of every pitch period);
+ *   cycle k = [onset k, onset k+1), length T_k, peak P_k = its largest sample;
+ *   mean_period = mean T_k, mean_peak = mean P_k, f0_hz = fs / mean_period,
+ *   jitter_pct  = 100 * mean |T_k - T_k-1| / mean_period   (local jitter),
+ *   shimmer_pct = 100 * mean |P_k - P_k-1| / mean_peak     (local shimmer);
+ * sums are exact integers, the quotients FP64 rounded to float.  With glottal noise put the thresholds above the
+ * noise (e.g. 25 % and 50 % of the amplitude).  flow may be host or device memory; stats is host memory. */
+typedef struct vs_flow_stats {
+    uint32_t onsets;       /* trigger events found                                       */
+    uint32_t cycles;       /* complete cycles = onsets - 1 (0 if flags != 0)             */
+    uint32_t flags;        /* VS_STATS_OVERFLOW: more than nsamp/16 + 4 onsets           */
+    float    f0_hz, jitter_pct, shimmer_pct, mean_period, mean_peak;
+} vs_flow_stats;
+#define VS_STATS_OVERFLOW 1u
+int vs_flow_analyze_batch(vs_ctx *ctx, const int16_t *flow, const uint64_t *offsets, const uint64_t *nsamp,
+                          const int32_t *fs, const int16_t *lo, const int16_t *hi, size_t n, vs_flow_stats *stats);
+
 /* SURVEY 8f N1 -- `vowel -n`: white noise added to already filtered PCM, IN PLACE (vowel_new.c:302-324).
  * Per stream and per frame of 50*((int)(fs*0.001/2.0)*2) samples: float power of the frame, uniform
  * noise of width sqrt(12*power/snr) drawn with random() seeded by srandom(seed[i]) (vowel_new.c:234),

@@ -142,3 +142,29 @@ def test_batch_driver_slabs_and_writer_pool(tools, golden, tmp_path):
     m.write_text(f"{tmp_path}/no_such_dir/x.wav a 1 -d 0.5\n")
     r = subprocess.run([str(tools / "vs_batch"), "-m", str(m)], capture_output=True, text=True)
     assert r.returncode != 0
+
+
+def test_acoustic_tool_measures_what_flowgen_made(tools, tmp_path):
+    """host/bin/acoustic on WAV files written by host/bin/flowgen_shimmer: its line per file carries the
+    statistics tests/analysis_ref.py computes from the same samples"""
+    import analysis_ref as ar
+    files = []
+    for k, args in enumerate(["-d 1 -f 110 -g 140 -j 2 -s 6", "-d 0.8 -f 201 -g 260", "-d 1.2 -f 87 -g 120 -j 0.5 -a 9000"]):
+        f = tmp_path / f"v{k}.wav"
+        r = subprocess.run([str(tools / "flowgen_shimmer"), "-o", str(f)] + args.split(), env=dict(os.environ, VS_SEED=str(100 + k)),
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        files.append(f)
+    r = subprocess.run([str(tools / "acoustic")] + [str(f) for f in files], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert len(lines) == len(files)
+    for f, line in zip(files, lines):
+        t = line.split()
+        want = ar.stats(payload(f), fs=22050)
+        assert t[0] == str(f) and int(t[1]) == 22050 and int(t[2]) == payload(f).size and int(t[3]) == want["cycles"]
+        for got, key, nd in zip(t[4:9], ("f0_hz", "jitter_pct", "shimmer_pct", "mean_period", "mean_peak"), (3, 4, 4, 3, 2)):
+            assert abs(float(got) - want[key]) <= 0.6 * 10 ** -nd + 1e-6 * abs(want[key]), (f.name, key, got, want[key])
+    # the second voice has neither jitter nor shimmer: its cycles are all alike
+    assert float(lines[1].split()[5]) == 0.0 and float(lines[1].split()[6]) == 0.0
+    assert "usage" in subprocess.run([str(tools / "acoustic"), "-l", "5", "-h", "2", str(files[0])], capture_output=True, text=True).stdout

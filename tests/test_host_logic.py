@@ -157,3 +157,27 @@ def test_two_rank_partition_over_gloo():
     assert rows[0][0] == 0 and rows[0][1] == rows[1][0] and rows[1][1] == 65536
     assert rows[0][3] < rows[1][2]                              # seed ranges do not overlap
     assert tmax == 2.0
+
+
+def test_analysis_restatement_trigger_is_the_sequential_one():
+    """tests/analysis_ref.py states vs_flow_analyze_batch's two-threshold trigger with array operations: it must be the
+    sequential state machine of include/voicesynth.h"""
+    import analysis_ref as ar
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        x = rng.integers(-5, 6, 257)
+        lo = int(rng.integers(-3, 2))
+        hi = lo + int(rng.integers(0, 3))
+        armed, want = True, []
+        for m, v in enumerate(x):
+            if v > hi:
+                if armed:
+                    want.append(m)
+                armed = False
+            elif v <= lo:
+                armed = True
+        assert list(ar.onsets(x, lo, hi)) == want
+    cycle = np.array([0] * 20 + [3, 9, 3] + [0] * 17, dtype=np.int16)
+    s = ar.stats(np.tile(cycle, 50), fs=8000)
+    assert s["cycles"] == 49 and s["mean_period"] == 40.0 and s["f0_hz"] == 200.0 and s["jitter_pct"] == 0.0 and s["mean_peak"] == 9.0
+    assert ar.stats(np.tile(np.array([0, 5], dtype=np.int16), 100))["flags"] == 1     # a cycle every 2 samples: flagged

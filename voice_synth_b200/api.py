@@ -21,6 +21,9 @@ PERIOD_DTYPE = np.dtype([("T", "<i4"), ("T2", "<i4"), ("T3", "<i4"), ("T4", "<i4
                          ("S", "<f4"), ("ndraws", "<i4"), ("ndw", "<i4"), ("x_pow", "<f4"), ("w_pow", "<f4"),
                          ("reserved", "<u4"), ("start", "<u8")])
 assert PERIOD_DTYPE.itemsize == 56
+FLOW_STATS_DTYPE = np.dtype([("onsets", "<u4"), ("cycles", "<u4"), ("flags", "<u4"), ("f0_hz", "<f4"), ("jitter_pct", "<f4"),
+                             ("shimmer_pct", "<f4"), ("mean_period", "<f4"), ("mean_peak", "<f4")])
+assert FLOW_STATS_DTYPE.itemsize == 32
 
 _FLOW_FIELDS = [("dur", np.float32, 1.0), ("jitter", np.float32, 0.0), ("shimmer", np.float32, 0.0),
                 ("cq", np.float32, 0.55), ("K", np.float32, 0.65), ("Kvar", np.float32, 0.0), ("F0", np.float32, 120.0),
@@ -330,6 +333,20 @@ class Context:
         self._check(self.L.vs_vowel_noise_batch(self.h, _ptr(pcm), _ptr(offs), ns.ctypes.data, snr.ctypes.data,
                                                 _ptr(rate), sd.ctypes.data, n))
         return pcm
+
+    def flow_analyze_batch(self, flow, nsamp, offsets=None, fs=None, lo=None, hi=None):
+        """cycle-to-cycle analysis of glottal flow (include/voicesynth.h): F0, local jitter and shimmer
+        per stream as a structured array (FLOW_STATS_DTYPE). flow: numpy array or device tensor."""
+        ns = np.ascontiguousarray(nsamp, dtype=np.uint64)
+        n = len(ns)
+        offs = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.uint64)
+        rate = None if fs is None else np.ascontiguousarray(np.broadcast_to(np.asarray(fs, dtype=np.int32), (n,)))
+        tl = None if lo is None else np.ascontiguousarray(np.broadcast_to(np.asarray(lo, dtype=np.int16), (n,)))
+        th = None if hi is None else np.ascontiguousarray(np.broadcast_to(np.asarray(hi, dtype=np.int16), (n,)))
+        stats = np.zeros(n, dtype=FLOW_STATS_DTYPE)
+        self._check(self.L.vs_flow_analyze_batch(self.h, _ptr(flow), _ptr(offs), ns.ctypes.data, _ptr(rate), _ptr(tl), _ptr(th),
+                                                 n, stats.ctypes.data))
+        return stats
 
     def synth_batch(self, p, f, out=None, offsets=None, want_raw=False):
         if out is not None and offsets is None and want_raw is False:

@@ -39,6 +39,8 @@ cudaError_t vs_launch_flow_rows(const VsRenderArgs &a, cudaStream_t s);
 int vs_flow_rows_warps(void);
 cudaError_t vs_launch_fp64_peak(double *scratch, int blocks, int iters, cudaStream_t s);
 cudaError_t vs_launch_vnoise(int16_t *pcm, const VsNoiseRow *rows, uint32_t n_rows, cudaStream_t s);
+cudaError_t vs_launch_analyze(const int16_t *flow, const VsAnalyzeRow *rows, uint32_t n_rows, uint32_t *onsets, uint32_t *counts,
+                              vs_flow_stats *out, cudaStream_t s);
 
 namespace {
 
@@ -71,7 +73,7 @@ struct Slot {
     cudaEvent_t slab_done[2] = {nullptr, nullptr};   /* D2H of the slab using pcm[k] finished */
     cudaEvent_t slab_ready = nullptr;                /* render of the current slab finished   */
     DevBuf streams[VS_DEPTH], chunks[VS_DEPTH], order[VS_DEPTH], table[VS_DEPTH], snap[VS_DEPTH], nper[VS_DEPTH], status[VS_DEPTH];
-    DevBuf costab, pcm[2], raw[2], flowin[2], log, ticket;
+    DevBuf costab, pcm[2], raw[2], flowin[2], log, ticket, analyze;
     uint32_t ticket_base = 0;                        /* value of the row counter of vs_flow_rows_kernel before the next launch */
     PinBuf h_streams[VS_DEPTH], h_chunks[VS_DEPTH], h_order[VS_DEPTH], h_nper[VS_DEPTH], h_status[VS_DEPTH];
     size_t costab_uploaded = 0;
@@ -1408,7 +1410,7 @@ void vs_ctx_destroy(vs_ctx *ctx)
         if (s.copy2) cudaStreamSynchronize(s.copy2);
         if (s.copy) cudaStreamSynchronize(s.copy);
         for (int k = 0; k < 2; k++) if (s.plans[k]) cudaStreamSynchronize(s.plans[k]);
-        std::vector<DevBuf *> bufs = {&s.costab, &s.pcm[0], &s.pcm[1], &s.raw[0], &s.raw[1], &s.flowin[0], &s.flowin[1], &s.log};
+        std::vector<DevBuf *> bufs = {&s.costab, &s.pcm[0], &s.pcm[1], &s.raw[0], &s.raw[1], &s.flowin[0], &s.flowin[1], &s.log, &s.ticket, &s.analyze};
         std::vector<PinBuf *> pins;
         for (int k = 0; k < VS_DEPTH; k++) {
             for (DevBuf *b : {&s.streams[k], &s.chunks[k], &s.order[k], &s.table[k], &s.snap[k], &s.nper[k], &s.status[k]}) bufs.push_back(b);
@@ -1646,6 +1648,58 @@ int vs_vowel_noise_batch(vs_ctx *ctx, int16_t *pcm, const uint64_t *offsets, con
         }
     }
     CU(cudaStreamSynchronize(sl.compute));                    /* `rows` is pageable host memory */
+    return VS_OK;
+}
+
+int vs_flow_analyze_batch(vs_ctx *ctx, const int16_t *flow, const uint64_t *offsets, const uint64_t *nsamp, const int32_t *fs,
+                          const int16_t *lo, const int16_t *hi, size_t n, vs_flow_stats *stats)
+{
+    if (!ctx || !flow || !nsamp || !stats) return VS_EINVAL;
+    if (n == 0) return VS_OK;
+    if (n > 0x7fffffffull) return fail(ctx, VS_EINVAL, "too many streams");
+    int rc = vs_sync(ctx);                                    /* the flow may be the output of a call still in flight */
+    if (rc) return rc;
+    DeviceGuard restore_device;
+    Slot &sl = ctx->slots[0];
+    CU(cudaSetDevice(sl.dev));
+    std::vector<VsAnalyzeRow> rows(n);
+    uint64_t max_n = 0, first = ~0ull, last = 0, slots = 0;
+    for (size_t i = 0; i < n; i++) max_n = std::max(max_n, nsamp[i]);
+    for (size_t i = 0; i < n; i++) {
+        if (nsamp[i] > 0x7fffffffull) return fail(ctx, VS_EOVERLAP, "stream %zu: too many samples", i);
+        const int32_t rate = fs ? fs[i] : 22050;
+        if (rate <= 0) return fail(ctx, VS_ERANGE, "stream %zu: sampling rate", i);
+        const int16_t tl = lo ? lo[i] : (int16_t)0, th = hi ? hi[i] : (int16_t)0;
+        if (tl > th) return fail(ctx, VS_ERANGE, "stream %zu: thresholds lo > hi", i);
+        VsAnalyzeRow &r = rows[i];
+        r.off = offsets ? offsets[i] : (uint64_t)i * max_n;
+        r.n = (uint32_t)nsamp[i];
+        r.cap = r.n / 16u + 4u;
+        r.ons_off = slots;
+        r.fs = rate; r.lo = tl; r.hi = th;
+        slots += r.cap;
+        first = std::min(first, r.off);
+        last = std::max(last, r.off + r.n);
+    }
+    int dev = -1;
+    const bool on_dev = classify(flow, &dev) == PK_DEVICE;
+    if (on_dev && dev != sl.dev) return fail(ctx, VS_EINVAL, "device buffer lives on device %d, ctx on %d", dev, sl.dev);
+    /* scratch: rows | per-stream onset counts | stats | onset lists */
+    const size_t rows_b = (n * sizeof(VsAnalyzeRow) + 255) & ~(size_t)255, cnt_b = (n * sizeof(uint32_t) + 255) & ~(size_t)255;
+    const size_t st_b = (n * sizeof(vs_flow_stats) + 255) & ~(size_t)255;
+    if ((rc = dev_reserve(ctx, sl, sl.analyze, rows_b + cnt_b + st_b + slots * sizeof(uint32_t)))) return rc;
+    unsigned char *base = (unsigned char *)sl.analyze.p;
+    CU(cudaMemcpyAsync(base, rows.data(), n * sizeof(VsAnalyzeRow), cudaMemcpyHostToDevice, sl.compute));
+    const int16_t *d_flow = flow;
+    if (!on_dev) {
+        if ((rc = dev_reserve(ctx, sl, sl.pcm[0], (last - first) * sizeof(int16_t) + 256))) return rc;
+        d_flow = (const int16_t *)sl.pcm[0].p - first;
+        CU(cudaMemcpyAsync(sl.pcm[0].p, flow + first, (last - first) * sizeof(int16_t), cudaMemcpyHostToDevice, sl.compute));
+    }
+    CU(vs_launch_analyze(d_flow, (const VsAnalyzeRow *)base, (uint32_t)n, (uint32_t *)(base + rows_b + cnt_b + st_b),
+                         (uint32_t *)(base + rows_b), (vs_flow_stats *)(base + rows_b + cnt_b), sl.compute));
+    CU(cudaMemcpyAsync(stats, base + rows_b + cnt_b, n * sizeof(vs_flow_stats), cudaMemcpyDeviceToHost, sl.compute));
+    CU(cudaStreamSynchronize(sl.compute));                    /* `rows` and `stats` are the caller's / pageable memory */
     return VS_OK;
 }
 

@@ -148,4 +148,14 @@ struct VsNoiseRow {
     uint32_t seed;
 };
 
+/* flow analysis (N4): one entry per stream */
+struct VsAnalyzeRow {
+    uint64_t off;          /* samples, relative to the flow pointer */
+    uint64_t ons_off;      /* first slot of the stream's onset list */
+    uint32_t n;
+    uint32_t cap;          /* slots in the onset list */
+    int32_t  fs;
+    int16_t  lo, hi;       /* trigger thresholds */
+};
+
 #endif
