@@ -119,15 +119,19 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_indices):
+        """ONE nvidia-smi for all the GPUs of the job, started by rank 0 (a sampler per rank means N processes taking
+        the driver's locks twenty times a second next to N ranks launching kernels)"""
         self.rows = []
         self.proc = None
-        self.gpu = gpu_index
+        self.gpus = list(gpu_indices)
 
     def start(self):
+        if not self.gpus:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-i", ",".join(str(g) for g in self.gpus)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -139,8 +143,18 @@ class ClockSampler:
     def stop(self):
         if self.proc:
             self.proc.terminate()
-        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 8 and r[1].isdigit())
         mx = [int(r[2]) for r in self.rows if len(r) >= 8 and r[2].isdigit()]
+        per_gpu = {}
+        for r in self.rows:
+            if len(r) >= 8 and r[1].isdigit():
+                per_gpu.setdefault(r[0], []).append(int(r[1]))
+        # per GPU the median of its busy samples; the job's figure is the slowest GPU's
+        meds = []
+        for v in per_gpu.values():
+            v.sort()
+            b = v[len(v) // 2:]
+            meds.append(b[len(b) // 2])
+        sm = sorted(x for v in per_gpu.values() for x in v)
         reasons = set()
         for r in self.rows:
             if len(r) >= 8:
@@ -148,9 +162,8 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(name)
         # the busy samples are the upper half (the sampler also sees idle gaps between steps)
-        busy = sm[len(sm) // 2:] if sm else []
-        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": min(meds) if meds else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "gpus": len(per_gpu)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -287,7 +300,7 @@ def main():
         ctx.synth_batch(p, f, out=host_out)
 
     # ---- value: device-resident ----------------------------------------------------------------
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(range(world) if rank == 0 else [])
     sampler.start()                      # runs across warm-up and both timed regions (nvidia-smi needs ~0.1 s to start)
     for _ in range(args.warmup):
         step_device()
@@ -412,11 +425,12 @@ def main():
     fp64_tflops, fp64_mhz = ctx.fp64_peak()
 
     # max over ranks; every rank's own e2e as well
-    e2e_all = [e2e_ms]
+    e2e_all, dev_all = [e2e_ms], [dev_ms]
     if world > 1:
-        gathered = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
-        dist.all_gather(gathered, torch.tensor([e2e_ms], dtype=torch.float64, device="cuda"))
+        gathered = [torch.zeros(2, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(gathered, torch.tensor([e2e_ms, dev_ms], dtype=torch.float64, device="cuda"))
         e2e_all = [float(g[0]) for g in gathered]
+        dev_all = [float(g[1]) for g in gathered]
     dev_ms, e2e_ms = max_over_ranks([dev_ms, e2e_ms])
     if rank != 0:
         if world > 1:
@@ -441,7 +455,8 @@ def main():
     gen_name = "branch-free" if path & 1 else "general"
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(dev_ms, 4), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": round(dev_ms, 4), "ms_per_step_per_rank": [round(m, 4) for m in dev_all],
+        "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "cfg2: 4096 streams x 1 s (22050 samples) per GPU, presets a,i,u,1..7 round-robin, F0 80-237.5 Hz, "
                                "jitter 0-3.5 %, shimmer 0-7.5 %, fused vs_synth_batch",

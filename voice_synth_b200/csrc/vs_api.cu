@@ -1481,6 +1481,7 @@ int vs_sync(vs_ctx *ctx)
         CU(cudaStreamSynchronize(s.compute));
         CU(cudaStreamSynchronize(s.copy2));
         CU(cudaStreamSynchronize(s.copy));
+        s.last_enqueue = {};                                  /* the device is idle: the next call may take the latency form of the plan kernel */
         for (int k = 0; k < VS_DEPTH; k++)
             if (s.h_status[k].p && *(int32_t *)s.h_status[k].p) { status = *(int32_t *)s.h_status[k].p; *(int32_t *)s.h_status[k].p = 0; }
     }
