@@ -74,6 +74,7 @@ struct Slot {
     cudaEvent_t slab_ready = nullptr;                /* render of the current slab finished   */
     DevBuf streams[VS_DEPTH], chunks[VS_DEPTH], order[VS_DEPTH], table[VS_DEPTH], snap[VS_DEPTH], nper[VS_DEPTH], status[VS_DEPTH];
     DevBuf costab, pcm[2], raw[2], flowin[2], log, ticket, analyze;
+    unsigned burst = 0;                              /* calls since one found the device idle */
     uint32_t ticket_base = 0;                        /* value of the row counter of vs_flow_rows_kernel before the next launch */
     PinBuf h_streams[VS_DEPTH], h_chunks[VS_DEPTH], h_order[VS_DEPTH], h_nper[VS_DEPTH], h_status[VS_DEPTH];
     size_t costab_uploaded = 0;
@@ -1138,7 +1139,13 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                     const auto now = std::chrono::steady_clock::now();
                     if (std::chrono::duration<double, std::milli>(now - sl.last_enqueue).count() < 2.0) busy = true;
                     sl.last_enqueue = now;
-                    plan_warps = pa.n_streams <= (busy ? VS_PLAN_WARP_MAX : any_noise ? VS_PLAN_WARP_MAX_NOISE : VS_PLAN_WARP_MAX_IDLE);
+                    /* the second call of a burst that began on an idle device: its plan must be ready when the first
+                     * call's render ends, one render time from now -- the thread form (0.39 ms on the bench batch, and it
+                     * has to wait for free SMs behind the first call's warp-form plan) would be late by a quarter of a
+                     * step, and every call behind it too until the pipeline has settled */
+                    sl.burst = busy ? sl.burst + 1u : 0u;
+                    const bool early = busy && sl.burst == 1u && !any_noise;     /* (with glottal noise the warp form is too heavy to share the SMs with a render: cfg3 157 -> 150 Gsamples/s) */
+                    plan_warps = pa.n_streams <= (busy && !early ? VS_PLAN_WARP_MAX : any_noise ? VS_PLAN_WARP_MAX_NOISE : VS_PLAN_WARP_MAX_IDLE);
                 }
                 CU(vs_launch_plan(pa, want_log, plan_warps, pstream));
                 ctx->timing.launches++;
