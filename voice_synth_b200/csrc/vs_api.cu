@@ -896,19 +896,20 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         for (size_t k = 0; k < n_slabs; k++) {
             sl.plan_slab_r0[k] = order.size();
             std::vector<uint32_t> ids(slab_c0[k + 1] - slab_c0[k]);
-            for (size_t c = 0; c < ids.size(); c++) ids[c] = (uint32_t)(slab_c0[k] + c);
             auto preset_of = [&](uint32_t c) -> int { return b.mode == VS_MODE_FLOW ? 0 : hs[s0 + hc[c].stream].preset; };
-            std::sort(ids.begin(), ids.end(), [&](uint32_t x, uint32_t y) {
-                const int px = preset_of(x), py = preset_of(y);
-                if (px != py) return px < py;
-                /* (flow-only chunks are all about one length: keep rows that share a pulse table together instead) */
-                const uint32_t wx = b.mode == VS_MODE_FLOW ? 0u : (hc[x].emit_hi - hc[x].gen_target) >> 6;
-                const uint32_t wy = b.mode == VS_MODE_FLOW ? 0u : (hc[y].emit_hi - hc[y].gen_target) >> 6;
-                if (wx != wy) return wx > wy;
-                const uint32_t tx = hs[s0 + hc[x].stream].pulse_off, ty = hs[s0 + hc[y].stream].pulse_off;
-                if (tx != ty) return tx < ty;
-                return x < y;
-            });
+            {   /* sort by one 64-bit key per row (preset, work descending, pulse table), then by id: the comparator of a
+                 * sort over the descriptors themselves cost 2.6 ms per 16 384 rows */
+                std::vector<std::pair<uint64_t, uint32_t>> keyed(ids.size());
+                for (size_t c = 0; c < ids.size(); c++) {
+                    const uint32_t id = (uint32_t)(slab_c0[k] + c);
+                    /* (flow-only chunks are all about one length: keep rows that share a pulse table together instead) */
+                    const uint32_t work = b.mode == VS_MODE_FLOW ? 0u : (hc[id].emit_hi - hc[id].gen_target) >> 6;
+                    keyed[c] = {((uint64_t)preset_of(id) << 60) | ((uint64_t)(0x0fffffffu - std::min(work, 0x0fffffffu)) << 32) |
+                                    (uint64_t)hs[s0 + hc[id].stream].pulse_off, id};
+                }
+                std::sort(keyed.begin(), keyed.end());
+                for (size_t c = 0; c < ids.size(); c++) ids[c] = keyed[c].second;
+            }
             Slot::PlanGeom &gm = sl.plan_geom[k];
             const size_t r_first = order.size();
             size_t i0 = 0;
