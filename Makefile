@@ -33,5 +33,5 @@ ptxas-info:
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o /dev/null $(CSRC)/vs_render.cu
 
 clean:
-	rm -rf $(LIBDIR) host/bin oracle/_build
+	rm -rf $(LIBDIR) $(OBJDIR) host/bin oracle/_build
 .PHONY: all lib host oracle clean ptxas-info

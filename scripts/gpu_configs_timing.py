@@ -1,4 +1,4 @@
-"""timing of BASELINE.json's other configurations on one B200 (device-resident output): python tests/gpu_configs_timing.py"""
+"""timing of BASELINE.json's other configurations on one B200 (device-resident output): python scripts/gpu_configs_timing.py"""
 import sys, pathlib
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
 import numpy as np, torch

@@ -1,4 +1,4 @@
-"""ad-hoc GPU smoke + timing (not a pytest file): python tests/gpu_quick.py"""
+"""ad-hoc GPU smoke + timing (not a pytest file): python scripts/gpu_quick.py"""
 import sys, time, pathlib
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
 import numpy as np

@@ -1,4 +1,4 @@
-"""A/B timing of debug switches (option 100) on the bench workload: python tests/prof_ab.py"""
+"""A/B timing of debug switches (option 100) on the bench workload: python scripts/prof_ab.py"""
 import sys, pathlib
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
 import torch

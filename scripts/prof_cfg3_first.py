@@ -1,4 +1,4 @@
-"""host time of the first calls of a cfg3 shard (allocation / first-touch effects): python tests/prof_cfg3_first.py"""
+"""host time of the first calls of a cfg3 shard (allocation / first-touch effects): python scripts/prof_cfg3_first.py"""
 import sys, pathlib, time
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
 import torch

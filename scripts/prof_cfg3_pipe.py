@@ -1,5 +1,5 @@
 """cfg3 shard, pipelined calls on a device buffer (what bench.py's other_workloads.cfg3 times), optionally after the
-things bench.py does first: python tests/prof_cfg3_pipe.py [stream] [dev] [host] [flow] [filt]"""
+things bench.py does first: python scripts/prof_cfg3_pipe.py [stream] [dev] [host] [flow] [filt]"""
 import sys, pathlib, time
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
 import numpy as np

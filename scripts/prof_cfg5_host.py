@@ -1,4 +1,4 @@
-"""host-side cost of the cfg5 calls (16 384 new utterances per call): VS_PROFILE_HOST=1 python tests/prof_cfg5_host.py"""
+"""host-side cost of the cfg5 calls (16 384 new utterances per call): VS_PROFILE_HOST=1 python scripts/prof_cfg5_host.py"""
 import sys, pathlib, time
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
 import torch

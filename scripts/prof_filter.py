@@ -1,4 +1,4 @@
-"""filter-only call on device-resident flow (for ncu): python tests/prof_filter.py"""
+"""filter-only call on device-resident flow (for ncu): python scripts/prof_filter.py"""
 import sys, pathlib
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
 import numpy as np, torch

@@ -1,4 +1,4 @@
-"""the bench loop (same call, device output, no sync in between) with host-side section times: python tests/prof_loop.py"""
+"""the bench loop (same call, device output, no sync in between) with host-side section times: python scripts/prof_loop.py"""
 import os, sys, pathlib, time
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
 import torch

@@ -1,4 +1,4 @@
-"""plan-kernel timing, one thread vs one warp per stream, over batch sizes: python tests/prof_plan.py"""
+"""plan-kernel timing, one thread vs one warp per stream, over batch sizes: python scripts/prof_plan.py"""
 import sys, pathlib
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
 import numpy as np, torch

@@ -1,4 +1,4 @@
-"""plan kernel time (thread form) for the bench batch on an otherwise idle GPU: python tests/prof_plan_nt.py"""
+"""plan kernel time (thread form) for the bench batch on an otherwise idle GPU: python scripts/prof_plan_nt.py"""
 import sys, pathlib
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
 import torch

@@ -1,5 +1,5 @@
 """how long do K pipelined calls of the bench batch take from an idle device: total = ramp + K x step
-python tests/prof_ramp.py"""
+python scripts/prof_ramp.py"""
 import sys, pathlib
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
 import torch

@@ -1,6 +1,6 @@
 """five pipelined steps of the bench workload between cudaProfilerStart/Stop, for
    ncu --replay-mode application-range (DRAM bytes of whole steps, kernels overlapping as they do in the bench):
-   python tests/prof_range.py [steps]"""
+   python scripts/prof_range.py [steps]"""
 import sys, pathlib
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
 import torch

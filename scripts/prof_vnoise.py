@@ -1,4 +1,4 @@
-"""vowel -n on the bench batch (4096 x 22050 samples, device-resident): python tests/prof_vnoise.py"""
+"""vowel -n on the bench batch (4096 x 22050 samples, device-resident): python scripts/prof_vnoise.py"""
 import sys, pathlib, time
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
 import numpy as np, torch
