@@ -349,6 +349,22 @@ def main():
     launches += t["launches"] * args.steps
     ctx.set_option(api.OPT_ASYNC_HOST, 0)
 
+    # the ceiling of that number: the same bytes as plain device-to-host copies into the same pinned buffer, all ranks at
+    # once (on an 8-GPU box the GPUs share PCIe switches: the per-rank rate is a property of the box, not of the library)
+    cs = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(cs):
+        host_out_t.copy_(dev_out, non_blocking=True)
+    cs.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(cs):
+        for _ in range(5):
+            host_out_t.copy_(dev_out, non_blocking=True)
+    cs.synchronize()
+    copy_ms = (time.perf_counter() - t0) * 1e3 / 5
+    barrier()
+
     # ---- the two stand-alone kernels on the same batch (device-resident): vs_flowgen_batch, vs_vowel_filter_batch ----
     def best_render(fn, reps=6):
         best = None
@@ -425,12 +441,13 @@ def main():
     fp64_tflops, fp64_mhz = ctx.fp64_peak()
 
     # max over ranks; every rank's own e2e as well
-    e2e_all, dev_all = [e2e_ms], [dev_ms]
+    e2e_all, dev_all, copy_all = [e2e_ms], [dev_ms], [copy_ms]
     if world > 1:
-        gathered = [torch.zeros(2, dtype=torch.float64, device="cuda") for _ in range(world)]
-        dist.all_gather(gathered, torch.tensor([e2e_ms, dev_ms], dtype=torch.float64, device="cuda"))
+        gathered = [torch.zeros(3, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(gathered, torch.tensor([e2e_ms, dev_ms, copy_ms], dtype=torch.float64, device="cuda"))
         e2e_all = [float(g[0]) for g in gathered]
         dev_all = [float(g[1]) for g in gathered]
+        copy_all = [float(g[2]) for g in gathered]
     dev_ms, e2e_ms = max_over_ranks([dev_ms, e2e_ms])
     if rank != 0:
         if world > 1:
@@ -467,7 +484,11 @@ def main():
                    "other_workloads": other},
         "e2e": {"value": round(e2e, 1), "unit": "Msamples/s", "ms_per_step": round(e2e_ms, 3),
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "per_rank_Msamples_s": [round(samples_per_step / (m * 1e-3) / 1e6, 1) for m in e2e_all]},
+                "per_rank_Msamples_s": [round(samples_per_step / (m * 1e-3) / 1e6, 1) for m in e2e_all],
+                "plain_copy": {"what": "the same 180.6 MB per rank as bare cudaMemcpyAsync device-to-host into the same pinned buffer, all ranks at once",
+                               "per_rank_GBs": [round(2.0 * samples_per_step / (m * 1e-3) / 1e9, 2) for m in copy_all],
+                               "Msamples_s": round(total_samples / (max(copy_all) * 1e-3) / 1e6, 1),
+                               "e2e_over_plain_copy": round(max(copy_all) / e2e_ms, 4)}},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": f"vs_render_kernel<SYNTH> ({gen_name} generator, one launch per step)",
                      "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
