@@ -30,7 +30,7 @@
 enum { VS_MODE_FLOW = 0, VS_MODE_SYNTH = 1, VS_MODE_FILTER = 2 };
 enum { VS_GEN_FAST = 0, VS_GEN_SIMPLE = 1 };
 enum { VS_FILT_INT = 0, VS_FILT_FMA = 1, VS_FILT_EXACT = 2 };
-cudaError_t vs_launch_plan(const VsPlanArgs &a, bool want_log, bool warp_per_stream, cudaStream_t s);
+cudaError_t vs_launch_plan(const VsPlanArgs &a, bool want_log, bool need_pulse, bool warp_per_stream, cudaStream_t s);
 cudaError_t vs_launch_render(const VsRenderArgs &a, int mode, int gen, bool noise, int filt, cudaStream_t s);
 cudaError_t vs_render_init_device();
 int vs_render_window(int mode);
@@ -516,7 +516,7 @@ uint32_t choose_chunk(vs_ctx *ctx, const Slot &slot, int mode, size_t n_streams,
  * chunk length  L_s = budget - W_s  and pick the smallest budget whose rows fit in `waves` waves;
  * take the wave count with the smallest  waves * budget. */
 void plan_filter_chunks(vs_ctx *ctx, const Slot &slot, const std::vector<VsStream> &hs, size_t a0, size_t a1,
-                        std::vector<uint32_t> &nchunks)
+                        std::vector<uint32_t> &nchunks, int plan_nt)
 {
     const size_t ns = a1 - a0;
     nchunks.assign(ns, 1u);
@@ -529,7 +529,7 @@ void plan_filter_chunks(vs_ctx *ctx, const Slot &slot, const std::vector<VsStrea
     }
     /* rows per wave; a few SMs stay free for the plan kernels of the next two calls (one CTA of VS_PLAN_NT streams per
      * SM each, see VS_PLAN_SMEM) */
-    const int plan_ctas = (int)((ns + VS_PLAN_NT - 1) / VS_PLAN_NT);
+    const int plan_ctas = (int)((ns + (size_t)plan_nt - 1) / (size_t)plan_nt);
     const int reserve = vs_plan_reserve(plan_ctas);
     const int render_sms = slot.sm_count > 4 * VS_PLAN_SMS ? slot.sm_count - reserve : slot.sm_count;
     const double cap = (double)render_sms * VS_NT;
@@ -773,7 +773,9 @@ int run_batch(vs_ctx *ctx, const Batch &b)
     const int compact = (any_kvar || want_log) ? VS_TAB_FULL : !any_noise ? VS_TAB_C8 : noise_simple ? VS_TAB_N16 : VS_TAB_FULL;
     /* flow without glottal noise: lanes along the row (vs_flow_rows_kernel).  T2 >= 2: row_validate() bounds A*K then */
     const bool flow_rows = b.mode == VS_MODE_FLOW && compact == VS_TAB_C8 && amp_fits && !ctx->opt_simple_gen && t_min >= 24 && fc.t2_min >= 2;
-    const uint64_t ph_mask = flow_rows ? 63u : 7u;           /* rows keep their position inside a 128-byte line / a 16-byte piece */
+    const uint64_t ph_mask = flow_rows ? 63u : 7u;
+    /* streams per CTA of the thread-form plan kernel: without glottal noise and period log its lean form (vs_plan.cu) */
+    const int plan_nt = (any_noise || want_log) ? VS_PLAN_NT : VS_PLAN_NT_LEAN;           /* rows keep their position inside a 128-byte line / a 16-byte piece */
 
     /* ---- 4. per slot: descriptors up, then slabs of plan -> render -> copy ------------------- */
     for (size_t g = 0; g < nslots; g++) {
@@ -811,7 +813,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
         const bool known_plan = same_inputs && sl.plan_for_version == ctx->in_version;     /* same bytes as the call that made the plan */
         if (!known_plan) {
         sig.reserve(3 * ns + 8);
-        sig.push_back(((uint64_t)b.mode << 48) ^ ((uint64_t)n_slabs << 24) ^ (uint64_t)slab_streams);
+        sig.push_back(((uint64_t)b.mode << 48) ^ ((uint64_t)n_slabs << 24) ^ (uint64_t)slab_streams ^ ((uint64_t)plan_nt << 52));
         sig.push_back((uint64_t)(int64_t)ctx->opt_chunk ^ ((uint64_t)ctx->opt_exact << 62) ^ ((uint64_t)sl.sm_count << 40));
         { double t = ctx->opt_tol, w = ctx->opt_warps; uint64_t u; memcpy(&u, &t, 8); sig.push_back(u); memcpy(&u, &w, 8); sig.push_back(u); }
         for (size_t i = s0; i < s1; i++) {
@@ -836,7 +838,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             for (size_t i = a0; i < a1; i++) tot += hs[i].n;
             const uint32_t Lflow = b.mode == VS_MODE_FLOW ? choose_chunk(ctx, sl, b.mode, a1 - a0, tot, 0.0, flow_rows) : 0u;
             std::vector<uint32_t> nch;
-            if (b.mode != VS_MODE_FLOW) plan_filter_chunks(ctx, sl, hs, a0, a1, nch);
+            if (b.mode != VS_MODE_FLOW) plan_filter_chunks(ctx, sl, hs, a0, a1, nch, plan_nt);
             slab_c0[k] = hc.size();
             for (size_t i = a0; i < a1; i++) {
                 VsStream &s = hs[i];
@@ -1148,7 +1150,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
                     const bool early = busy && sl.burst == 1u && !any_noise;     /* (with glottal noise the warp form is too heavy to share the SMs with a render: cfg3 157 -> 150 Gsamples/s) */
                     plan_warps = pa.n_streams <= (busy && !early ? VS_PLAN_WARP_MAX : any_noise ? VS_PLAN_WARP_MAX_NOISE : VS_PLAN_WARP_MAX_IDLE);
                 }
-                CU(vs_launch_plan(pa, want_log, plan_warps, pstream));
+                CU(vs_launch_plan(pa, want_log, any_noise || want_log, plan_warps, pstream));
                 ctx->timing.launches++;
             }
         }
@@ -1227,7 +1229,7 @@ int run_batch(vs_ctx *ctx, const Batch &b)
             {   /* persistent grid: one CTA per render SM (the plan kernels of the next calls own the others); the
                  * flow-only kernel is small, a few of its CTAs share an SM */
                 const uint32_t blocks = (ra.n_rows / 32u + 3u) / 4u;
-                const int plan_ctas = (int)((ns + VS_PLAN_NT - 1) / VS_PLAN_NT);
+                const int plan_ctas = (int)((ns + (size_t)plan_nt - 1) / (size_t)plan_nt);
                 const int reserve = vs_plan_reserve(plan_ctas);
                 const uint32_t sms = (uint32_t)std::max(1, sl.sm_count - reserve);
                 uint32_t per_sm = 1;

@@ -12,6 +12,7 @@
                                   CTA cannot share an SM with a render CTA: the plan kernel of call k+1 runs on
                                   the VS_PLAN_SMS SMs the chunk planner keeps free, instead of being starved of
                                   issue slots by the render warps of call k (measured: 0.35 -> 0.7 ms)        */
+#define VS_PLAN_NT_LEAN 1024   /* ... of its form without the open phase (no glottal noise, no period log): 64 registers */
 #define VS_PLAN_SMEM (96 * 1024)
 #define VS_PLAN_SMS  32         /* most SMs the chunk planner leaves to the plan kernels of the next two calls */
 /* batches up to this many streams get one WARP per stream in the plan kernel (vs_api.cu, plan launch) */

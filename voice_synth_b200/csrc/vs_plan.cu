@@ -70,21 +70,24 @@ __device__ __forceinline__ void vs_store_period(void *table, int fmt, uint64_t i
     }
 }
 
-template <bool LOG>
-__global__ void __launch_bounds__(VS_PLAN_NT, 1) vs_plan_kernel(const VsPlanArgs a)
+/* PULSE: some stream of the batch needs the open phase evaluated in the plan (glottal noise, period log).  Without it
+ * the kernel is the two random walks alone and fits 64 registers: NT = 1024 streams per CTA, half the SMs kept off
+ * the render kernel */
+template <bool LOG, bool PULSE, int NT>
+__global__ void __launch_bounds__(NT, 1) vs_plan_kernel(const VsPlanArgs a)
 {
-    extern __shared__ __align__(16) uint32_t s_rng[];                  /* [31][VS_PLAN_NT] RNG states (+ padding up to VS_PLAN_SMEM) */
-    const uint32_t s = blockIdx.x * VS_PLAN_NT + threadIdx.x;
+    extern __shared__ __align__(16) uint32_t s_rng[];                  /* [31][NT] RNG states (+ padding up to VS_PLAN_SMEM) */
+    const uint32_t s = blockIdx.x * NT + threadIdx.x;
     if (s >= a.n_streams) return;
     const VsStream st = a.streams[s];
     VsRng g;
     g.r = s_rng + threadIdx.x;
-    vs_rng_seed<VS_PLAN_NT>(g, st.seed);                                             /* flowgen_shimmer.c:241 */
+    vs_rng_seed<NT>(g, st.seed);                                             /* flowgen_shimmer.c:241 */
 
     const bool do_jit = (st.flags & VS_F_JITTER) && st.jitter != 0.0f;    /* :248 */
     const bool do_shm = (st.flags & VS_F_SHIMMER) && st.shimmer != 0.0f;  /* :295 */
-    const bool noise = (st.flags & VS_F_NOISE) != 0;                      /* :373 */
-    const bool pulse = LOG || noise;
+    const bool noise = PULSE && (st.flags & VS_F_NOISE) != 0;             /* :373 */
+    const bool pulse = PULSE && (LOG || noise);
     const int P = st.P, T2 = st.T2;
     const float Pf = (float)P, ampf = (float)st.amp;
     const float t_hi = __fmul_rn(1.2f, Pf), t_lo = __fmul_rn(0.8f, Pf);
@@ -112,7 +115,7 @@ __global__ void __launch_bounds__(VS_PLAN_NT, 1) vs_plan_kernel(const VsPlanArgs
             const double prev = (double)dper;
             float cur;
             do {
-                const int32_t r = vs_rng_next<VS_PLAN_NT>(g); nd++;
+                const int32_t r = vs_rng_next<NT>(g); nd++;
                 double t = vs_div_const((double)r, VS_RM4, VS_INV_RM4);
                 t = __dmul_rn(__dmul_rn(t, 40000.0), jit);
                 const double J = (double)__double2float_rn(__dsub_rn(t, jit2));
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(VS_PLAN_NT, 1) vs_plan_kernel(const VsPlanArgs
             const double prev = (double)dsh;
             float cur;
             do {
-                const int32_t r = vs_rng_next<VS_PLAN_NT>(g); nd++;
+                const int32_t r = vs_rng_next<NT>(g); nd++;
                 const float eps = __fmul_rn((float)r, 4.656612873077393e-10f);   /* / (float)RAND_MAX == * 2^-31, exact */
                 S = __double2float_rn(__dsub_rn(__dmul_rn(__dmul_rn((double)eps, 4.0), shm), shm2));
                 const double den = __dsub_rn(2.0, (double)S);
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(VS_PLAN_NT, 1) vs_plan_kernel(const VsPlanArgs
         if (T < 1 || T > 32767) { atomicExch(a.status, VS_ERANGE); return; }
 
         /* closure-speed draw, always consumed (:325) */
-        const int32_t rk = vs_rng_next<VS_PLAN_NT>(g); nd++;
+        const int32_t rk = vs_rng_next<NT>(g); nd++;
         const double kq = __dsub_rn(vs_div_const((double)rk, VS_RAND_MAX_D, VS_INV_RM), 0.5);
         const float Knew = __double2float_rn(__dmul_rn(Kbase, __dadd_rn(1.0, __dmul_rn(kv2, kq))));
 
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(VS_PLAN_NT, 1) vs_plan_kernel(const VsPlanArgs
         while (next_target < count + (uint32_t)T) {
             chunks[next_c].first_period = np;
             chunks[next_c].first_start = count;
-            if (noise && a.rng_snap) vs_rng_save<VS_PLAN_NT>(g, a.rng_snap + (size_t)(st.chunk0 + next_c) * 32);
+            if (noise && a.rng_snap) vs_rng_save<NT>(g, a.rng_snap + (size_t)(st.chunk0 + next_c) * 32);
             next_c++;
             next_target = next_c < st.n_chunks ? chunks[next_c].gen_target : 0xffffffffu;
         }
@@ -196,12 +199,12 @@ __global__ void __launch_bounds__(VS_PLAN_NT, 1) vs_plan_kernel(const VsPlanArgs
                 if (LOG) {
                     float wa = 0.0f;
                     for (uint32_t k = 0; k < n_noise; k++) {
-                        const int w = vs_noise_w(vs_rng_next<VS_PLAN_NT>(g), ndw);
+                        const int w = vs_noise_w(vs_rng_next<NT>(g), ndw);
                         wa = __fadd_rn(wa, __fmul_rn((float)w, (float)w));
                     }
                     w_pow = __fdiv_rn(wa, (float)T);
                 } else {
-                    vs_rng_skip<VS_PLAN_NT>(g, n_noise);
+                    vs_rng_skip<NT>(g, n_noise);
                 }
             }
         }
@@ -648,7 +651,7 @@ cudaError_t vs_launch_fp64_peak(double *scratch, int blocks, int iters, cudaStre
 /* ------------------------------------------------------------------------------------------------
  * launch wrappers (called from vs_api.cu)
  * ---------------------------------------------------------------------------------------------- */
-cudaError_t vs_launch_plan(const VsPlanArgs &a, bool want_log, bool warp_per_stream, cudaStream_t s)
+cudaError_t vs_launch_plan(const VsPlanArgs &a, bool want_log, bool need_pulse, bool warp_per_stream, cudaStream_t s)
 {
     if (warp_per_stream && !want_log) {
         vs_plan_warp_kernel<<<(a.n_streams + VS_PLANW_NT / 32 - 1) / (VS_PLANW_NT / 32), VS_PLANW_NT, 0, s>>>(a);
@@ -657,11 +660,16 @@ cudaError_t vs_launch_plan(const VsPlanArgs &a, bool want_log, bool warp_per_str
     const unsigned grid = (a.n_streams + VS_PLAN_NT - 1) / VS_PLAN_NT;
     static_assert(VS_PLAN_SMEM >= VS_RNG_DEG * VS_PLAN_NT * 4, "plan kernel shared memory");
     if (want_log) {
-        cudaFuncSetAttribute(vs_plan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_PLAN_SMEM);
-        vs_plan_kernel<true><<<grid, VS_PLAN_NT, VS_PLAN_SMEM, s>>>(a);
+        cudaFuncSetAttribute(vs_plan_kernel<true, true, VS_PLAN_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_PLAN_SMEM);
+        vs_plan_kernel<true, true, VS_PLAN_NT><<<grid, VS_PLAN_NT, VS_PLAN_SMEM, s>>>(a);
+    } else if (need_pulse) {
+        cudaFuncSetAttribute(vs_plan_kernel<false, true, VS_PLAN_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_PLAN_SMEM);
+        vs_plan_kernel<false, true, VS_PLAN_NT><<<grid, VS_PLAN_NT, VS_PLAN_SMEM, s>>>(a);
     } else {
-        cudaFuncSetAttribute(vs_plan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_PLAN_SMEM);
-        vs_plan_kernel<false><<<grid, VS_PLAN_NT, VS_PLAN_SMEM, s>>>(a);
+        constexpr int smem = VS_RNG_DEG * VS_PLAN_NT_LEAN * 4;
+        static_assert(smem >= VS_PLAN_SMEM, "the lean plan CTA must not share an SM with a render CTA either");
+        cudaFuncSetAttribute(vs_plan_kernel<false, false, VS_PLAN_NT_LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        vs_plan_kernel<false, false, VS_PLAN_NT_LEAN><<<(a.n_streams + VS_PLAN_NT_LEAN - 1) / VS_PLAN_NT_LEAN, VS_PLAN_NT_LEAN, smem, s>>>(a);
     }
     return cudaGetLastError();
 }
