@@ -300,7 +300,15 @@ def main():
         ctx.synth_batch(p, f, out=host_out)
 
     # ---- value: device-resident ----------------------------------------------------------------
-    sampler = ClockSampler(range(world) if rank == 0 else [])
+    def gpu_ids():                      # nvidia-smi does not honour CUDA_VISIBLE_DEVICES: name the job's GPUs by UUID
+        ids = []
+        for i in range(min(world, torch.cuda.device_count())):
+            try:
+                ids.append("GPU-" + str(torch.cuda.get_device_properties(i).uuid))
+            except Exception:
+                ids.append(str(i))
+        return ids
+    sampler = ClockSampler(gpu_ids() if rank == 0 else [])
     sampler.start()                      # runs across warm-up and both timed regions (nvidia-smi needs ~0.1 s to start)
     for _ in range(args.warmup):
         step_device()
