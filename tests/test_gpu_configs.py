@@ -414,3 +414,41 @@ def test_random_parameter_fuzz(ctx, vs, oracle):
     flow, foffs, ns = ctx.flowgen_batch(p0)
     pcm, offs, _ = ctx.synth_batch(p0, f0)
     _check_sample(oracle, vs, p0, f0, pcm, offs, ns, range(p0.n), flow, foffs)
+
+
+def test_carry_tolerance_option(ctx, vs, oracle):
+    """VS_OPT_CARRY_TOL trades chunk warm-up for carry error: the warm-up of every preset shrinks as the tolerance
+    grows, and at 1e-11 (ten times the default) the chunked FP64 waveform is still within 1e-5 of the oracle's and the PCM
+    within 1 LSB"""
+    n = 20
+    args = [f"-d 1.5 -f {90 + 9 * i} -g {130 + 9 * i} -j {0.5 + 0.1 * i:.1f} -s {2 + 0.3 * i:.1f}" for i in range(n)]
+    p = vs.FlowParams.from_cli(args, list(range(700, 700 + n)))
+    f = vs.FilterParams(n, ("aiu1234567" * 2)[:n])
+    want = []
+    for i in range(n):
+        o_pcm, o_raw = oracle.vowel(oracle.flowgen(_opar(oracle, vs, p, i)), chr(f.preset[i]), gain=float(f.gain[i]), pre=float(f.pre[i]), want_raw=True)
+        want.append((o_pcm, o_raw))
+    warm, extra = {}, {}
+    try:
+        for tol in (1e-12, 1e-11, 1e-9):
+            ctx.set_option(vs.OPT_CARRY_TOL, tol)
+            ctx.set_option(vs.OPT_CHUNK_SAMPLES, 4096)
+            warm[tol] = [ctx.filter_warmup(k) for k in "aiu1234567"]
+            pcm, offs, ns, raw = ctx.synth_batch(p, f, want_raw=True)
+            t = ctx.timing()
+            assert t["chunks"] > 3 * n
+            extra[tol] = t["warmup_samples"]
+            worst = 0.0
+            for i in range(n):
+                a0, a1 = int(offs[i]), int(offs[i]) + int(ns[i])
+                worst = max(worst, float(np.abs(raw[a0:a1] - want[i][1]).max()))
+                if tol <= 1e-11:
+                    assert int(np.abs(pcm[a0:a1].astype(np.int32) - want[i][0].astype(np.int32)).max()) <= 1, (tol, i)
+            print(f"carry tolerance {tol:g}: warm-up {min(warm[tol])}..{max(warm[tol])} samples, {extra[tol]} extra samples, waveform error {worst:.2e}")
+            if tol <= 1e-11:
+                assert worst <= 1e-5, (tol, worst)
+    finally:
+        ctx.set_option(vs.OPT_CARRY_TOL, 1e-12)
+        ctx.set_option(vs.OPT_CHUNK_SAMPLES, 0)
+    assert all(a > b > c for a, b, c in zip(warm[1e-12], warm[1e-11], warm[1e-9]))
+    assert extra[1e-12] > extra[1e-11] > extra[1e-9]
