@@ -260,7 +260,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from voice_synth_b200 import api, workloads
+    from voice_synth_b200 import api, sharding, workloads
 
     if args.warmup < 3:
         args.warmup = 3
@@ -283,7 +283,7 @@ def main():
 
     # the rank's share of the job: its own 4096 streams (distinct seeds), nothing is exchanged
     p, f = workloads.cfg2(n=N_STREAMS)
-    p.seed[...] = (1000 + rank * N_STREAMS + np.arange(N_STREAMS)).astype(np.uint32)
+    p.seed[...] = sharding.rank_seeds(N_STREAMS, rank)
     ns = api.flow_nsamples(p)
     samples_per_step = int(ns.sum())
 
